@@ -1,0 +1,183 @@
+/*
+ * skm_b200.h — C ABI of the B200-native Snekmer hot path (libskm_b200.so).
+ *
+ * The reference (PNNL-CompBio/Snekmer 1.3.0) is pure Python and has no FFI; the
+ * boundary it exposes is the Python module API (snekmer.vectorize.KmerVec,
+ * snekmer.alphabet, snekmer.io) and the rule-body loops in snekmer/rules/*.smk.
+ * Each entry point below names the reference code it replaces (file:line under
+ * /root/reference).  The Python package snekmer_b200 binds these with ctypes
+ * (snekmer_b200/_native.py); INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types in any signature;
+ *   - every d_* pointer is DEVICE memory owned by the caller; the library never
+ *     allocates persistent device memory; scratch comes from the caller through
+ *     (workspace, workspace_bytes) sized by the matching *_workspace() query;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     and re-entrant; no call synchronises the device unless stated;
+ *   - return 0 on success, a negative SKM_ERR_* otherwise; skm_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - sequences are a packed byte buffer `d_residues[nres]` (ASCII, base
+ *     pointer 16-byte aligned) plus `d_offsets[nseq+1]` (int64, offsets[0]=0 is
+ *     not required: offsets are positions in d_residues);
+ *   - k-mer codes: code = sum_i sym_i * nsym^(k-1-i) with sym_i the index of
+ *     the reduced symbol in the *sorted* output-symbol string; nsym^k <= 2^64.
+ */
+#ifndef SKM_B200_H
+#define SKM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(SKM_BUILDING)
+#define SKM_API __attribute__((visibility("default")))
+#else
+#define SKM_API
+#endif
+
+#define SKM_OK 0
+#define SKM_ERR_INVALID (-1)     /* bad argument */
+#define SKM_ERR_CUDA (-2)        /* CUDA runtime error (message has the string) */
+#define SKM_ERR_UNSUPPORTED (-3) /* valid request outside the built envelope */
+#define SKM_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define SKM_INVALID_SYMBOL 0xFF
+#define SKM_DENSE_MAX_SPACE (1ll << 27) /* largest nsym^k handled by table kernels */
+
+typedef void *skm_stream_t; /* cudaStream_t */
+
+/* library / device ------------------------------------------------------- */
+SKM_API int skm_version(void);
+SKM_API const char *skm_last_error(void);
+/* sm_count, compute capability of the current device */
+SKM_API int skm_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* (a1) residue -> symbol LUT.  Replaces the dict lookups of
+ * alphabet.py:88-96 (FULL_ALPHABETS) + vectorize.py:193-195 (translate) +
+ * vectorize.py:247 (char_set test).  map_from[i] -> map_to[i] for i < nmap;
+ * symbols = sorted output symbols.  A byte is valid iff its translated
+ * character is one of `symbols` (unmapped bytes translate to themselves).
+ * Host-only, no CUDA. */
+SKM_API int skm_lut_build(const char *map_from, const char *map_to, int nmap,
+                  const char *symbols, int nsym, uint8_t lut_out[256]);
+
+/* (a3) reduce(): vectorize.py:173-195 on the packed buffer — byte-wise
+ * translate with a 256-entry char map (rstrip('*') is applied by the caller on
+ * the offsets: it only shortens the strings). */
+SKM_API int skm_reduce_bytes(const uint8_t *d_residues, int64_t nres,
+                     const uint8_t *d_charmap, uint8_t *d_out,
+                     skm_stream_t stream);
+
+/* (a5/a6) KmerVec._kmer_gen / reduce_vectorize, vectorize.py:239-249,292-328:
+ * code of the window starting at every residue position, or all-ones
+ * (0xFFFFFFFF / 0xFFFFFFFFFFFFFFFF) where the window is invalid, crosses the
+ * end of its sequence or the position belongs to no sequence.
+ * code_bits = 32 requires nsym^k < 2^32, 64 requires nsym^k <= 2^64 - 1. */
+SKM_API int skm_encode_windows(const uint8_t *d_residues, int64_t nres,
+                       const int64_t *d_offsets, int64_t nseq,
+                       const uint8_t *d_lut, int nsym, int k, int code_bits,
+                       void *d_codes_out, skm_stream_t stream);
+
+/* (a7) basis construction, kmerize.smk:89-104, pass 1 over the FASTA.
+ * Accumulates into caller-initialised tables over the code space S = nsym^k
+ * (S <= SKM_DENSE_MAX_SPACE): d_count[c] += occurrences (init 0),
+ * d_first[c] = min(res_base + position of window start) (init all-ones).
+ * res_base is the global residue position of d_residues[0] so that several
+ * shards / GPUs can be merged by sum / min before skm_basis_finalize. */
+SKM_API int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres,
+                         const int64_t *d_offsets, int64_t nseq,
+                         const uint8_t *d_lut, int nsym, int k,
+                         uint64_t res_base, uint64_t *d_count,
+                         uint64_t *d_first, skm_stream_t stream);
+
+/* kmerize.smk:102-104 + dict insertion order: keep codes with
+ * count > min_filter, order by first occurrence.  Writes d_basis_codes[0..K),
+ * d_basis_counts[0..K), d_col_of_code[c] = column or -1 for every c < S, and K
+ * to *d_K (device int64).  Capacity of the two basis arrays: S. */
+SKM_API size_t skm_basis_finalize_workspace(int64_t S);
+SKM_API int skm_basis_finalize(const uint64_t *d_count, const uint64_t *d_first,
+                       int64_t S, int64_t min_filter, uint64_t *d_basis_codes,
+                       uint64_t *d_basis_counts, int32_t *d_col_of_code,
+                       int64_t *d_K, void *workspace, size_t workspace_bytes,
+                       skm_stream_t stream);
+
+/* kmerize.smk:72-78 (basis.txt branch) / learn on a given kmerlist:
+ * d_col_of_code[c] = j for c = d_basis_codes[j], -1 elsewhere. */
+SKM_API int skm_basis_colmap(const uint64_t *d_basis_codes, int64_t K, int64_t S,
+                     int32_t *d_col_of_code, skm_stream_t stream);
+
+/* (a9/a11) per-sequence k-mer counts over the basis, dense rows:
+ * kmerize.smk:112-120 (presence = counts > 0), learn.smk:359-383,
+ * apply.smk:195-206.  d_counts is [nseq, K] row-major; out_bits 32 (int32)
+ * or 16 (uint16, requires max_len <= 65535).  d_col_of_code may be NULL for
+ * the identity basis (column = code, K = S).  max_len = longest sequence
+ * (0 = unknown: 32-bit shared-memory counters are used). */
+SKM_API int skm_count_dense(const uint8_t *d_residues, int64_t nres,
+                    const int64_t *d_offsets, int64_t nseq,
+                    const uint8_t *d_lut, int nsym, int k,
+                    const int32_t *d_col_of_code, int64_t S, int64_t K,
+                    int out_bits, void *d_counts, int64_t max_len,
+                    skm_stream_t stream);
+
+/* same counts as CSR for large bases (learn.smk:359-383 at K ~ 1e6): per
+ * sequence the sorted distinct columns (or codes when d_col_of_code is NULL;
+ * nsym^k < 2^32) and their counts.  d_rowptr is int64 [nseq+1] (nnz =
+ * d_rowptr[nseq]); d_cols / d_vals need capacity nres (an upper bound of nnz).
+ * One call handles < 2^30 residues. */
+SKM_API size_t skm_count_csr_workspace(int64_t nres, int64_t nseq);
+SKM_API int skm_count_csr(const uint8_t *d_residues, int64_t nres,
+                  const int64_t *d_offsets, int64_t nseq, const uint8_t *d_lut,
+                  int nsym, int k, const int32_t *d_col_of_code, int64_t S,
+                  int64_t *d_rowptr, uint32_t *d_cols, int32_t *d_vals,
+                  void *workspace, size_t workspace_bytes,
+                  skm_stream_t stream);
+
+/* (a12/a13) learn: Library.filter_and_construct + _process_annotation_counts,
+ * learn.smk:316-326,385-408, fused with the per-sequence counting of
+ * learn.smk:359-383 (counts are never materialised):
+ *   M[a,:]     = sum of the count rows of the sequences with d_ann_id[s] == a
+ *   M[n_ann,:] = the same sum over sequences with d_ann_id[s] < 0 (unannotated,
+ *                or the earlier copies of a duplicated id) — the "rest" row
+ *   totals[:]  = column sum of all n_ann+1 rows = Totals over ALL sequences
+ *                (learn.smk:380).
+ * d_order (nullable) is a permutation of 0..nseq-1 that groups equal
+ * annotation ids (a stable sort by id): each CTA then adds one shared-memory
+ * row per run to M, so the reduction is contention-free and, being integer,
+ * bit-reproducible.  d_M is int64 [n_ann+1, K], d_totals int64 [K]; both are
+ * overwritten.  K*4 bytes must fit shared memory (K <= 51200). */
+SKM_API int skm_learn_dense(const uint8_t *d_residues, int64_t nres,
+                    const int64_t *d_offsets, int64_t nseq,
+                    const uint8_t *d_lut, int nsym, int k,
+                    const int32_t *d_col_of_code, int64_t S, int64_t K,
+                    const int32_t *d_ann_id, const int64_t *d_order,
+                    int64_t n_ann, int64_t *d_M, int64_t *d_totals,
+                    skm_stream_t stream);
+
+/* (a16/a17) apply: cosine_similarity + top-2, apply.smk:278-335 and
+ * learn.smk:811-849.  Queries are int32 count rows [nq, K] over the same
+ * columns as d_M (int64 [n_ann, K]); d_qnorm2 holds ||q||^2 over ALL valid
+ * query k-mers (the union re-index of apply.smk:268-276), d_mnorm2 ||m||^2.
+ * Outputs per query: top-1 / top-2 annotation index (ties: lowest index) and
+ * cosine in float64.  Dot products are exact integers. */
+SKM_API size_t skm_apply_dense_workspace(int64_t nq, int64_t n_ann, int64_t K);
+SKM_API int skm_apply_dense(const int32_t *d_Q, int64_t nq, int64_t K,
+                    const int64_t *d_M, int64_t n_ann, const double *d_qnorm2,
+                    const double *d_mnorm2, int32_t *d_top1, int32_t *d_top2,
+                    double *d_score1, double *d_score2, double *d_scores_full,
+                    void *workspace, size_t workspace_bytes,
+                    skm_stream_t stream);
+
+/* row squared norms of an integer matrix (sklearn normalize, float64). */
+SKM_API int skm_row_norm2_i32(const int32_t *d_X, int64_t rows, int64_t cols,
+                      double *d_out, skm_stream_t stream);
+SKM_API int skm_row_norm2_i64(const int64_t *d_X, int64_t rows, int64_t cols,
+                      double *d_out, skm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKM_B200_H */

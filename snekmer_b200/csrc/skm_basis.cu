@@ -1,0 +1,247 @@
+// skm_basis.cu — kernel (b'): k-mer basis construction (kmerize.smk:89-104).
+//
+// Pass 1 of the reference's vectorize rule builds {kmer: total count} in
+// first-occurrence (dict insertion) order and keeps count > min_filter.  Here:
+//   skm_basis_accumulate  count[c] += 1, first[c] = min(global position) over
+//                         all valid windows, for the code space S = nsym^k;
+//   skm_basis_finalize    keep count > min_filter, order by `first`.
+// Keeping `first` as the global residue position (res_base + index in the
+// packed buffer) makes shards mergeable by (sum, min) — the multi-GPU exchange.
+//
+// Small code spaces (S <= SMALL_S) are privatised per CTA in shared memory
+// (counts and first positions relative to the CTA's contiguous residue range)
+// and flushed with S atomics per CTA; large ones go straight to L2 atomics
+// (low contention because the table is large) with a read-before-min filter.
+// Algorithmic bytes: R residues + 8 (N+1) offsets + 24 S table.
+#include <cub/cub.cuh>
+
+#include "skm_common.cuh"
+
+namespace skm {
+
+constexpr int64_t SMALL_S = 16384;   // 8 B per code of shared memory -> 128 KB
+
+__device__ __forceinline__ int64_t lower_bound_off(const int64_t *__restrict__ off, int64_t n, int64_t target) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// CTA i owns the sequences whose start lies in [R*i/G, R*(i+1)/G): contiguous and residue-balanced.
+__device__ __forceinline__ void cta_seq_range(const int64_t *__restrict__ off, int64_t nseq, int64_t *lo, int64_t *hi) {
+    const int64_t r0 = __ldg(off), r1 = __ldg(off + nseq);
+    const int64_t span = r1 - r0;
+    const int64_t G = gridDim.x, i = blockIdx.x;
+    const int64_t t0 = r0 + (int64_t)(((__int128)span * i) / G);
+    const int64_t t1 = r0 + (int64_t)(((__int128)span * (i + 1)) / G);
+    *lo = lower_bound_off(off, nseq, t0);
+    *hi = (i + 1 == G) ? nseq : lower_bound_off(off, nseq, t1);
+    if (i == 0) *lo = 0;
+}
+
+template <typename CodeT, int NW>
+__global__ void __launch_bounds__(256) basis_small_kernel(const uint8_t *__restrict__ res, int64_t nres,
+                                                          const int64_t *__restrict__ off, int64_t nseq,
+                                                          const uint8_t *__restrict__ lut, int nsym, int k, int S,
+                                                          uint64_t res_base, unsigned long long *__restrict__ g_count,
+                                                          unsigned long long *__restrict__ g_first) {
+    extern __shared__ __align__(16) uint32_t s_tab[];   // [S] counts, [S] relative first positions
+    __shared__ uint8_t s_lut[256];
+    __shared__ int64_t s_range[2];
+    __shared__ unsigned int s_next;
+    uint32_t *s_cnt = s_tab, *s_min = s_tab + S;
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }
+    if (threadIdx.x == 0) { cta_seq_range(off, nseq, &s_range[0], &s_range[1]); s_next = 0; }
+    __syncthreads();
+    const int64_t lo = s_range[0], hi = s_range[1];
+    const int lane = threadIdx.x & 31;
+    if (lo < hi) {
+        const int64_t base = __ldg(off + lo);            // relative positions fit 32 bits (host sizes the grid)
+        for (;;) {
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(&s_next, 1u);
+            t = __shfl_sync(FULL, t, 0);
+            const int64_t s = lo + t;
+            if (s >= hi) break;
+            const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
+            warp_scan_sequence<CodeT, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t g, CodeT code, bool ok) {
+                if (ok) {
+                    atomicAdd(&s_cnt[code], 1u);
+                    const uint32_t rel = uint32_t(g - base);
+                    if (rel < s_min[code]) atomicMin(&s_min[code], rel);
+                }
+            });
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const uint32_t c = s_cnt[i];
+            if (c) {
+                atomicAdd(g_count + i, (unsigned long long)c);
+                atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(base) + s_min[i]));
+            }
+        }
+    }
+}
+
+template <typename CodeT, int NW>
+__global__ void __launch_bounds__(256) basis_large_kernel(const uint8_t *__restrict__ res, int64_t nres,
+                                                          const int64_t *__restrict__ off, int64_t nseq,
+                                                          const uint8_t *__restrict__ lut, int nsym, int k,
+                                                          uint64_t res_base, unsigned long long *__restrict__ g_count,
+                                                          unsigned long long *__restrict__ g_first) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nseq; s += nwarps) {
+        const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
+        warp_scan_sequence<CodeT, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t g, CodeT code, bool ok) {
+            if (ok) {
+                atomicAdd(g_count + code, 1ull);
+                const unsigned long long pos = res_base + uint64_t(g);
+                // stale reads can only be too large (first is monotone decreasing): never skips a needed min
+                if (pos < __ldcg(g_first + code)) atomicMin(g_first + code, pos);
+            }
+        });
+    }
+}
+
+__global__ void basis_keys_kernel(const uint64_t *__restrict__ count, const uint64_t *__restrict__ first, int64_t S,
+                                  uint64_t min_filter, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < S; i += int64_t(gridDim.x) * blockDim.x) {
+        keys[i] = (count[i] > min_filter) ? first[i] : ~0ull;
+        vals[i] = uint64_t(i);
+    }
+}
+
+// after the sort: kept codes come first, ordered by first occurrence
+__global__ void basis_emit_kernel(const uint64_t *__restrict__ keys_sorted, const uint64_t *__restrict__ codes_sorted,
+                                  const uint64_t *__restrict__ count, int64_t S, uint64_t *__restrict__ basis_codes,
+                                  uint64_t *__restrict__ basis_counts, int32_t *__restrict__ col_of_code,
+                                  int64_t *__restrict__ K_out) {
+    for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < S; j += int64_t(gridDim.x) * blockDim.x) {
+        const uint64_t key = keys_sorted[j], code = codes_sorted[j];
+        const bool kept = key != ~0ull;
+        if (kept) {
+            basis_codes[j] = code;
+            basis_counts[j] = count[code];
+            if (col_of_code) col_of_code[code] = (int32_t)j;
+            const bool last = (j + 1 == S) || (keys_sorted[j + 1] == ~0ull);
+            if (last) *K_out = j + 1;
+        } else {
+            if (col_of_code) col_of_code[code] = -1;
+            if (j == 0) *K_out = 0;
+        }
+    }
+}
+
+__global__ void colmap_fill_kernel(int32_t *col, int64_t S) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < S; i += int64_t(gridDim.x) * blockDim.x) col[i] = -1;
+}
+__global__ void colmap_scatter_kernel(const uint64_t *__restrict__ codes, int64_t K, int64_t S, int32_t *col) {
+    for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < K; j += int64_t(gridDim.x) * blockDim.x) {
+        const uint64_t c = codes[j];
+        if (c < (uint64_t)S) col[c] = (int32_t)j;
+    }
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace skm
+
+extern "C" {
+
+int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                         const uint8_t *d_lut, int nsym, int k, uint64_t res_base, uint64_t *d_count,
+                         uint64_t *d_first, skm_stream_t stream) {
+    using namespace skm;
+    int rc = check_common(d_residues, nres, d_offsets, nseq, d_lut, nsym, k);
+    if (rc) return rc;
+    unsigned __int128 S128;
+    code_space(nsym, k, &S128);
+    if (S128 > (unsigned __int128)SKM_DENSE_MAX_SPACE) {
+        set_error("skm_basis_accumulate: code space %d^%d exceeds the table limit 2^27 (use the sorted path)", nsym, k);
+        return SKM_ERR_UNSUPPORTED;
+    }
+    if (!d_count || !d_first) { set_error("skm_basis_accumulate: NULL table"); return SKM_ERR_INVALID; }
+    if (nseq == 0 || nres == 0) return SKM_OK;
+    const int64_t S = (int64_t)S128;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nw = neighbour_words(k);
+    auto *cnt = reinterpret_cast<unsigned long long *>(d_count);
+    auto *fst = reinterpret_cast<unsigned long long *>(d_first);
+    if (S <= SMALL_S) {
+        const size_t smem = size_t(S) * 8;
+        int64_t grid = int64_t(sm_count()) * (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
+        const int64_t min_grid = (nres >> 30) + 1;       // keep each CTA's residue range well below 2^32
+        if (grid < min_grid) grid = min_grid;
+        SKM_DISPATCH_NW(nw, {
+            auto kern = basis_small_kernel<uint32_t, NW>;
+            SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)grid, 256, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, (int)S, res_base, cnt, fst);
+        });
+    } else {
+        const int grid = sm_count() * 8;
+        SKM_DISPATCH_NW(nw, (basis_large_kernel<uint32_t, NW><<<grid, 256, 0, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, res_base, cnt, fst)));
+    }
+    SKM_LAUNCH_CHECK("basis_accumulate");
+    return SKM_OK;
+}
+
+size_t skm_basis_finalize_workspace(int64_t S) {
+    using namespace skm;
+    if (S <= 0) return 256;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)S);
+    return 4 * align_up(size_t(S) * 8) + align_up(temp) + 256;
+}
+
+int skm_basis_finalize(const uint64_t *d_count, const uint64_t *d_first, int64_t S, int64_t min_filter,
+                       uint64_t *d_basis_codes, uint64_t *d_basis_counts, int32_t *d_col_of_code, int64_t *d_K,
+                       void *workspace, size_t workspace_bytes, skm_stream_t stream) {
+    using namespace skm;
+    if (S <= 0 || S > SKM_DENSE_MAX_SPACE) { set_error("skm_basis_finalize: S=%lld out of range", (long long)S); return SKM_ERR_INVALID; }
+    if (!d_count || !d_first || !d_basis_codes || !d_basis_counts || !d_K) { set_error("skm_basis_finalize: NULL argument"); return SKM_ERR_INVALID; }
+    if (min_filter < 0) min_filter = 0;   // count > negative is always true for present k-mers; absent ones (count 0) must stay out
+    const size_t need = skm_basis_finalize_workspace(S);
+    if (!workspace || workspace_bytes < need) { set_error("skm_basis_finalize: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t seg = align_up(size_t(S) * 8);
+    char *p = reinterpret_cast<char *>(workspace);
+    p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255));
+    uint64_t *keys_in = (uint64_t *)p, *keys_out = (uint64_t *)(p + seg);
+    uint64_t *vals_in = (uint64_t *)(p + 2 * seg), *vals_out = (uint64_t *)(p + 3 * seg);
+    void *temp = p + 4 * seg;
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, vals_in, vals_out, S);
+    const int grid = (int)std::min<int64_t>((S + 255) / 256, int64_t(sm_count()) * 8);
+    basis_keys_kernel<<<grid, 256, 0, st>>>(d_count, d_first, S, (uint64_t)min_filter, keys_in, vals_in);
+    SKM_LAUNCH_CHECK("basis_keys_kernel");
+    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, S, 0, 64, st));
+    basis_emit_kernel<<<grid, 256, 0, st>>>(keys_out, vals_out, d_count, S, d_basis_codes, d_basis_counts, d_col_of_code, d_K);
+    SKM_LAUNCH_CHECK("basis_emit_kernel");
+    return SKM_OK;
+}
+
+int skm_basis_colmap(const uint64_t *d_basis_codes, int64_t K, int64_t S, int32_t *d_col_of_code, skm_stream_t stream) {
+    using namespace skm;
+    if (S <= 0 || S > SKM_DENSE_MAX_SPACE || K < 0 || !d_col_of_code || (K > 0 && !d_basis_codes)) { set_error("skm_basis_colmap: bad arguments"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>((S + 255) / 256, int64_t(sm_count()) * 8);
+    colmap_fill_kernel<<<grid, 256, 0, st>>>(d_col_of_code, S);
+    SKM_LAUNCH_CHECK("colmap_fill_kernel");
+    if (K > 0) {
+        const int g2 = (int)std::min<int64_t>((K + 255) / 256, int64_t(sm_count()) * 8);
+        colmap_scatter_kernel<<<g2, 256, 0, st>>>(d_basis_codes, K, S, d_col_of_code);
+        SKM_LAUNCH_CHECK("colmap_scatter_kernel");
+    }
+    return SKM_OK;
+}
+
+}  // extern "C"

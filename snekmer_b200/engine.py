@@ -1,0 +1,384 @@
+"""engine: batch entry points of the B200 hot path (host side of the C-ABI).
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed
+only; every computation below is a call into libskm_b200.so with raw device
+pointers.  All functions raise if CUDA or the library is unavailable — there is
+no CPU fallback.
+
+Data layout in HBM
+  residues  uint8 [R]    all sequences back to back (ASCII), 16-byte aligned
+  offsets   int64 [N+1]  sequence s is residues[offsets[s]:offsets[s+1]]
+  codes     uint32/uint64 base-|A| k-mer codes (symbols in sorted order)
+  basis     uint64 [K] codes in first-occurrence order (kmerize.smk:89-104)
+  col_of_code int32 [|A|^k]  code → basis column, -1 if filtered out
+  counts    int32/uint16 [N, K] row-major, or CSR (rowptr int64, cols uint32, vals int32)
+  M         int64 [A+1, K] annotation rows + one "rest" row; totals int64 [K]
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native
+from . import alphabet as _alphabet
+from ._native import SkmError, check, lib
+
+AlphabetT = Union[str, int, None]
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise SkmError(-101, "no CUDA device: snekmer_b200 has no CPU path (the oracle lives in oracle/ and is test-only)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise SkmError(-101, f"device {dev} is not a CUDA device")
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class AlphabetTables:
+    name: str
+    symbols: str
+    nsym: int
+    lut_host: bytes
+    lut: torch.Tensor          # uint8 [256] on device
+    charmap: torch.Tensor      # uint8 [256] on device
+
+
+_tables_cache = {}
+
+
+def alphabet_tables(alphabet: AlphabetT, device=None) -> AlphabetTables:
+    dev = _require_cuda(device)
+    name = _alphabet.get_alphabet_name(alphabet)
+    key = (name, dev.index, tuple(sorted(_alphabet.residue_map(name).items())))
+    hit = _tables_cache.get(key)
+    if hit is not None:
+        return hit
+    syms = _alphabet.symbols(name)
+    lut_host = _alphabet.lut(name)
+    t = AlphabetTables(
+        name=name, symbols=syms, nsym=len(syms), lut_host=lut_host,
+        lut=torch.frombuffer(bytearray(lut_host), dtype=torch.uint8).to(dev),
+        charmap=torch.frombuffer(bytearray(_alphabet.charmap(name)), dtype=torch.uint8).to(dev),
+    )
+    _tables_cache[key] = t
+    return t
+
+
+def code_space(nsym: int, k: int) -> int:
+    return nsym ** k
+
+
+class SequenceBatch:
+    """Packed sequences resident in HBM."""
+
+    def __init__(self, residues: torch.Tensor, offsets: torch.Tensor, offsets_host: np.ndarray):
+        assert residues.dtype == torch.uint8 and offsets.dtype == torch.int64
+        self.residues = residues
+        self.offsets = offsets
+        self.offsets_host = offsets_host
+        self.n = len(offsets_host) - 1
+        self.nres = int(offsets_host[-1]) if self.n >= 0 and len(offsets_host) else 0
+        lens = np.diff(offsets_host) if self.n > 0 else np.zeros(0, np.int64)
+        self.max_len = int(lens.max()) if lens.size else 0
+
+    @property
+    def device(self):
+        return self.residues.device
+
+    @staticmethod
+    def pack_host(seqs: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+        offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+        if len(seqs):
+            np.cumsum([len(s) for s in seqs], out=offs[1:])
+        buf = np.frombuffer("".join(seqs).encode("latin-1", "replace"), dtype=np.uint8)
+        return buf, offs
+
+    @classmethod
+    def from_packed(cls, residues: np.ndarray, offsets: np.ndarray, device=None, pinned: bool = False) -> "SequenceBatch":
+        dev = _require_cuda(device)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        nres = int(offsets[-1]) if len(offsets) else 0
+        # +16 bytes of slack keeps the buffer 16-byte granular; kernels never read past nres
+        d_res = torch.empty(max(nres, 1) + 16, dtype=torch.uint8, device=dev)
+        if nres:
+            src = torch.from_numpy(residues[:nres])
+            d_res[:nres].copy_(src, non_blocking=pinned)
+        d_off = torch.from_numpy(offsets).to(dev)
+        return cls(d_res, d_off, offsets)
+
+    @classmethod
+    def from_strings(cls, seqs: Sequence[str], device=None) -> "SequenceBatch":
+        buf, offs = cls.pack_host([str(s) for s in seqs])
+        return cls.from_packed(buf, offs, device)
+
+
+# ---------------------------------------------------------------------------
+# (a) encode
+# ---------------------------------------------------------------------------
+def encode_windows(batch: SequenceBatch, alphabet: AlphabetT, k: int) -> torch.Tensor:
+    """Code of the window starting at every residue (KmerVec.reduce_vectorize,
+    vectorize.py:292-328, for the whole batch).  Returns uint32-as-int32 or
+    uint64-as-int64 tensor [nres]; invalid windows are all-ones (-1)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    bits = 32 if S < 2 ** 32 else 64
+    out = torch.empty(max(batch.nres, 1), dtype=torch.int32 if bits == 32 else torch.int64, device=batch.device)
+    check(lib().skm_encode_windows(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut),
+                                   tab.nsym, int(k), bits, _ptr(out), _stream()))
+    return out[:batch.nres]
+
+
+def reduce_bytes(batch: SequenceBatch, alphabet: AlphabetT) -> torch.Tensor:
+    """reduce() (vectorize.py:173-195) on the packed buffer: translated bytes [nres]."""
+    tab = alphabet_tables(alphabet, batch.device)
+    out = torch.empty_like(batch.residues)
+    check(lib().skm_reduce_bytes(_ptr(batch.residues), batch.nres, _ptr(tab.charmap), _ptr(out), _stream()))
+    return out[:batch.nres]
+
+
+# ---------------------------------------------------------------------------
+# (b') basis
+# ---------------------------------------------------------------------------
+@dataclass
+class Basis:
+    """k-mer basis in first-occurrence order + the code→column map."""
+    alphabet: str
+    k: int
+    symbols: str
+    codes: torch.Tensor                 # int64 (uint64 bit pattern) [K]
+    counts: Optional[torch.Tensor]      # int64 [K] total occurrences, None for a supplied basis
+    col_of_code: torch.Tensor           # int32 [S]
+    K: int
+    S: int
+
+    def codes_host(self) -> np.ndarray:
+        return self.codes.cpu().numpy().view(np.uint64)
+
+    def kmers(self) -> np.ndarray:
+        return decode_kmers(self.codes_host(), self.symbols, self.k)
+
+
+def decode_kmers(codes: np.ndarray, symbols: str, k: int) -> np.ndarray:
+    """uint64 codes → '<Uk' strings (host-side formatting of the basis)."""
+    codes = np.asarray(codes, dtype=np.uint64)
+    if codes.size == 0:
+        return np.array([], dtype=f"<U{max(k, 1)}")
+    n = np.uint64(len(symbols))
+    sym = np.frombuffer(symbols.encode("latin-1"), dtype=np.uint8)
+    chars = np.empty((codes.size, k), dtype=np.uint8)
+    c = codes.copy()
+    for i in range(k - 1, -1, -1):
+        chars[:, i] = sym[(c % n).astype(np.int64)]
+        c //= n
+    return chars.view(f"S{k}").ravel().astype(f"<U{k}")
+
+
+def encode_kmers(kmers: Sequence[str], symbols: str, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """k-mer strings → (uint64 codes, ok mask).  ok is False for k-mers of the
+    wrong length or with foreign symbols (they can never match a window)."""
+    arr = np.asarray(list(kmers), dtype=str)
+    ok = np.ones(arr.size, dtype=bool)
+    codes = np.zeros(arr.size, dtype=np.uint64)
+    if arr.size == 0:
+        return codes, ok
+    idx = np.full(256, -1, dtype=np.int64)
+    for i, ch in enumerate(symbols):
+        idx[ord(ch)] = i
+    lens = np.char.str_len(arr)
+    ok &= lens == k
+    n = np.uint64(len(symbols))
+    safe = np.where(ok, arr, symbols[0] * k)
+    try:
+        raw = np.char.encode(safe, "latin-1")
+    except UnicodeEncodeError:
+        raw = np.array([s.encode("latin-1", "replace") for s in safe])
+    mat = np.frombuffer(raw.astype(f"S{k}").tobytes(), dtype=np.uint8).reshape(arr.size, k)
+    d = idx[mat]
+    ok &= (d >= 0).all(axis=1)
+    d = np.where(d < 0, 0, d).astype(np.uint64)
+    for i in range(k):
+        codes = codes * n + d[:, i]
+    return codes, ok
+
+
+def basis_tables(S: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fresh (count, first) accumulation tables over the code space."""
+    count = torch.zeros(S, dtype=torch.int64, device=device)
+    first = torch.full((S,), -1, dtype=torch.int64, device=device)   # all-ones = +inf as uint64
+    return count, first
+
+
+def basis_accumulate(batch: SequenceBatch, alphabet: AlphabetT, k: int, count: torch.Tensor, first: torch.Tensor,
+                     res_base: int = 0) -> None:
+    tab = alphabet_tables(alphabet, batch.device)
+    check(lib().skm_basis_accumulate(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut),
+                                     tab.nsym, int(k), int(res_base), _ptr(count), _ptr(first), _stream()))
+
+
+def basis_finalize(alphabet: AlphabetT, k: int, count: torch.Tensor, first: torch.Tensor, min_filter: int = 0) -> Basis:
+    dev = count.device
+    tab = alphabet_tables(alphabet, dev)
+    S = count.numel()
+    ws_bytes = lib().skm_basis_finalize_workspace(S)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    codes = torch.empty(S, dtype=torch.int64, device=dev)
+    counts = torch.empty(S, dtype=torch.int64, device=dev)
+    col = torch.empty(S, dtype=torch.int32, device=dev)
+    dK = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_basis_finalize(_ptr(count), _ptr(first), S, int(min_filter), _ptr(codes), _ptr(counts), _ptr(col),
+                                   _ptr(dK), _ptr(ws), ws_bytes, _stream()))
+    K = int(dK.item())
+    return Basis(tab.name, int(k), tab.symbols, codes[:K], counts[:K], col, K, S)
+
+
+def build_basis(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0) -> Basis:
+    """Pass 1 of the vectorize rule (kmerize.smk:89-104) for one shard."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    count, first = basis_tables(S, batch.device)
+    basis_accumulate(batch, alphabet, k, count, first, 0)
+    return basis_finalize(alphabet, k, count, first, min_filter)
+
+
+def basis_from_kmers(kmers: Sequence[str], alphabet: AlphabetT, k: int, device=None) -> Tuple[Basis, np.ndarray]:
+    """A supplied basis (basis.txt branch, kmerize.smk:72-78, or a learned
+    kmerlist).  Returns (Basis over the encodable k-mers, index of each of them
+    in the supplied list)."""
+    dev = _require_cuda(device)
+    tab = alphabet_tables(alphabet, dev)
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    codes, ok = encode_kmers(kmers, tab.symbols, k)
+    keep = np.flatnonzero(ok)
+    d_codes = torch.from_numpy(codes[keep].view(np.int64)).to(dev)
+    col = torch.empty(S, dtype=torch.int32, device=dev)
+    check(lib().skm_basis_colmap(_ptr(d_codes), len(keep), S, _ptr(col), _stream()))
+    return Basis(tab.name, int(k), tab.symbols, d_codes, None, col, len(keep), S), keep
+
+
+# ---------------------------------------------------------------------------
+# (b) counts
+# ---------------------------------------------------------------------------
+def count_dense(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis] = None,
+                dtype: torch.dtype = torch.int32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-sequence k-mer counts [N, K] over `basis` (None = identity basis: column = code)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    K = S if basis is None else basis.K
+    bits = {torch.int32: 32, torch.uint16: 16, torch.int16: 16}[dtype]
+    if out is None:
+        out = torch.empty((batch.n, K), dtype=dtype, device=batch.device)
+    else:
+        assert out.is_contiguous() and tuple(out.shape) == (batch.n, K) and out.dtype == dtype
+    check(lib().skm_count_dense(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
+                                int(k), None if basis is None else _ptr(basis.col_of_code), S, K, bits, _ptr(out),
+                                batch.max_len, _stream()))
+    return out
+
+
+def count_csr(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis] = None):
+    """Per-sequence sorted (column, count) pairs as CSR: (rowptr int64 [N+1], cols int32 [nnz], vals int32 [nnz])."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    dev = batch.device
+    ws_bytes = lib().skm_count_csr_workspace(batch.nres, batch.n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rowptr = torch.empty(batch.n + 1, dtype=torch.int64, device=dev)
+    cols = torch.empty(max(batch.nres, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(batch.nres, 1), dtype=torch.int32, device=dev)
+    check(lib().skm_count_csr(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
+                              int(k), None if basis is None else _ptr(basis.col_of_code), S, _ptr(rowptr), _ptr(cols),
+                              _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+    nnz = int(rowptr[-1].item()) if batch.n else 0
+    return rowptr, cols[:nnz].clone(), vals[:nnz].clone()
+
+
+# ---------------------------------------------------------------------------
+# (c) learn
+# ---------------------------------------------------------------------------
+def learn_dense(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis], ann_id: torch.Tensor,
+                n_ann: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-annotation summed counts.  ann_id int32 [N] (<0 = not in any row).
+    Returns (M int64 [n_ann+1, K] with the "rest" row last, totals int64 [K])."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    K = S if basis is None else basis.K
+    dev = batch.device
+    ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    assert ann_id.numel() == batch.n
+    # group equal ids: stable sort so that each annotation is one contiguous run
+    order = torch.sort(torch.where(ann_id < 0, torch.full_like(ann_id, n_ann), ann_id), stable=True).indices.contiguous()
+    M = torch.empty((n_ann + 1, K), dtype=torch.int64, device=dev)
+    totals = torch.empty(K, dtype=torch.int64, device=dev)
+    check(lib().skm_learn_dense(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
+                                int(k), None if basis is None else _ptr(basis.col_of_code), S, K, _ptr(ann_id),
+                                _ptr(order), int(n_ann), _ptr(M), _ptr(totals), _stream()))
+    return M, totals
+
+
+# ---------------------------------------------------------------------------
+# (d) apply
+# ---------------------------------------------------------------------------
+def row_norm2(X: torch.Tensor) -> torch.Tensor:
+    X = X.contiguous()
+    out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+    fn = {torch.int32: lib().skm_row_norm2_i32, torch.int64: lib().skm_row_norm2_i64}[X.dtype]
+    check(fn(_ptr(X), X.shape[0], X.shape[1], _ptr(out), _stream()))
+    return out
+
+
+@dataclass
+class ApplyResult:
+    top1: torch.Tensor      # int32 [Q]
+    top2: torch.Tensor      # int32 [Q] (-1 if fewer than 2 annotations)
+    score1: torch.Tensor    # float64 [Q]
+    score2: torch.Tensor    # float64 [Q]
+    scores: Optional[torch.Tensor] = None   # float64 [Q, A] when requested
+
+
+def apply_dense(Q: torch.Tensor, M: torch.Tensor, qnorm2: Optional[torch.Tensor] = None,
+                mnorm2: Optional[torch.Tensor] = None, full: bool = False, chunk: int = 1 << 16) -> ApplyResult:
+    """Cosine of every query count row against every annotation row + top-2
+    (apply.smk:278-335).  Q int32 [nq, K], M int64 [A, K]; qnorm2 defaults to the
+    norm over Q's own columns."""
+    dev = Q.device
+    Q = Q.contiguous()
+    M = M.contiguous()
+    nq, K = Q.shape
+    A = M.shape[0]
+    assert M.shape[1] == K and Q.dtype == torch.int32 and M.dtype == torch.int64
+    if qnorm2 is None:
+        qnorm2 = row_norm2(Q)
+    if mnorm2 is None:
+        mnorm2 = row_norm2(M)
+    top1 = torch.empty(nq, dtype=torch.int32, device=dev)
+    top2 = torch.empty(nq, dtype=torch.int32, device=dev)
+    s1 = torch.empty(nq, dtype=torch.float64, device=dev)
+    s2 = torch.empty(nq, dtype=torch.float64, device=dev)
+    scores = torch.empty((nq, A), dtype=torch.float64, device=dev) if full else None
+    chunk = max(1, min(chunk, nq))
+    ws_bytes = lib().skm_apply_dense_workspace(chunk, A, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for q0 in range(0, nq, chunk):
+        q1 = min(nq, q0 + chunk)
+        check(lib().skm_apply_dense(_ptr(Q[q0:q1]), q1 - q0, K, _ptr(M), A, _ptr(qnorm2[q0:q1]), _ptr(mnorm2),
+                                    _ptr(top1[q0:q1]), _ptr(top2[q0:q1]), _ptr(s1[q0:q1]), _ptr(s2[q0:q1]),
+                                    None if scores is None else _ptr(scores[q0:q1]), _ptr(ws), ws_bytes, _stream()))
+    return ApplyResult(top1, top2, s1, s2, scores)

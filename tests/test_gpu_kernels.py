@@ -1,0 +1,246 @@
+"""GPU parity tests: every CUDA kernel (through the C-ABI) against the CPU oracle
+and the reference-generated golden vectors.  Bit-exact for codes / bases /
+counts / learn matrices; cosine within 1e-12 absolute (float64 both sides; the
+stated tolerance of the path is 1e-5 relative)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import skm_oracle as O
+from util import GOLDEN, RULE_CONFIGS, csv_frame, edge_cases, load_rule, read_ann, read_fasta, unpack_vecs
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from snekmer_b200 import engine as E
+    from snekmer_b200 import alphabet as A
+
+
+def _alpha(a):
+    return None if a == "None" else (int(a) if str(a).isdigit() else a)
+
+
+def _rand_seqs(rng, n, lo=0, hi=600, p_x=0.002):
+    aa = np.array(list("ACDEFGHIKLMNPQRSTVWYXBZUO*acd"))
+    p = np.array([1.0] * 20 + [p_x * 20] * 9)
+    p /= p.sum()
+    return ["".join(rng.choice(aa, size=int(rng.integers(lo, hi)), p=p)) for _ in range(n)]
+
+
+def _codes_oracle(seqs, a, k):
+    lut, syms = O.build_lut(a)
+    res, offs = O.pack(seqs)
+    si, pos, code, valid = O.window_codes(res, offs, lut, len(syms), k)
+    full = np.full(len(res), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    g = offs[si] + pos
+    full[g[valid]] = code[valid]
+    return full, (si, pos, code, valid), (res, offs, lut, syms)
+
+
+def test_lut_matches_oracle():
+    for a in (0, 1, 2, 3, 4, 5, "ptm", None):
+        lut, syms = O.build_lut(a)
+        assert A.symbols(a) == syms
+        assert np.array_equal(np.frombuffer(A.lut(a), dtype=np.uint8), lut)
+
+
+@pytest.mark.parametrize("a", [0, 1, 2, 3, 4, 5, "ptm", "None"])
+def test_encode_edge_cases(a):
+    a = _alpha(a)
+    fx = edge_cases()
+    seqs = [s for _, s in fx["sequences"]]
+    batch = E.SequenceBatch.from_strings(seqs)
+    nsym = len(A.symbols(a))
+    for k in (1, 2, 3, 5, 8, 14):
+        if nsym ** k >= 2 ** 64:
+            with pytest.raises(E.SkmError):
+                E.encode_windows(batch, a, k)
+            continue
+        want, _, _ = _codes_oracle(seqs, a, k)
+        got = E.encode_windows(batch, a, k).cpu().numpy()
+        got = got.view(np.uint32).astype(np.uint64) if got.dtype == np.int32 else got.view(np.uint64)
+        if nsym ** k < 2 ** 32:
+            want = np.where(want == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF), want)
+        assert np.array_equal(got, want), (a, k)
+        # and the strings the reference API returns
+        case = fx["cases"][f"{'None' if a is None else a}:{k}"]
+        offs = batch.offsets_host
+        inv = np.uint64(0xFFFFFFFF if nsym ** k < 2 ** 32 else 0xFFFFFFFFFFFFFFFF)
+        for i in range(len(seqs)):
+            c = got[offs[i]:offs[i + 1]]
+            assert list(E.decode_kmers(c[c != inv], A.symbols(a), k)) == case["kmers"][i]
+
+
+@pytest.mark.parametrize("a,k", [(0, 1), (0, 16), (0, 31), (2, 8), (2, 20), (5, 3), (5, 9), (5, 19), (None, 2),
+                                 (None, 7), (None, 14), ("ptm", 6), ("ptm", 13), (1, 11), (3, 17), (4, 40), (0, 63)])
+def test_encode_random(a, k):
+    rng = np.random.default_rng(k * 131 + 7)
+    seqs = _rand_seqs(rng, 300, 0, 700)
+    seqs[5] = ""
+    seqs[17] = "A" * 1500
+    batch = E.SequenceBatch.from_strings(seqs)
+    want, _, (_, _, _, syms) = _codes_oracle(seqs, a, k)
+    got = E.encode_windows(batch, a, k).cpu().numpy()
+    if got.dtype == np.int32:
+        got = got.view(np.uint32).astype(np.uint64)
+        want = np.where(want == np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0xFFFFFFFF), want)
+    else:
+        got = got.view(np.uint64)
+    assert np.array_equal(got, want)
+
+
+def test_reduce_bytes():
+    rng = np.random.default_rng(3)
+    seqs = _rand_seqs(rng, 100, 0, 300)
+    batch = E.SequenceBatch.from_strings(seqs)
+    for a in (0, 3, 4, 5, None):
+        got = bytes(E.reduce_bytes(batch, a).cpu().numpy()).decode("latin-1")
+        want = "".join(O.reduce_str(s + "|", a)[:-1] for s in seqs)   # '|' guards rstrip: kernel keeps '*'
+        assert got == want
+
+
+@pytest.mark.parametrize("name", sorted(RULE_CONFIGS))
+def test_golden_rule_fixtures(name):
+    """vectorize → learn → apply on the reference-generated fixtures."""
+    a, k, mf = RULE_CONFIGS[name]
+    a = _alpha(a)
+    d = load_rule(name)
+    ann = read_ann(os.path.join(GOLDEN, "syn.ann"))
+    res_files = {}
+    for nb in ("synA", "synB"):
+        ids, seqs = read_fasta(os.path.join(GOLDEN, f"{nb}.fasta"))
+        batch = E.SequenceBatch.from_strings(seqs)
+        basis = E.build_basis(batch, a, k, mf)
+        assert list(basis.kmers()) == list(d[f"{nb}_kmerlist"])
+        C = E.count_dense(batch, a, k, basis)
+        assert np.array_equal((C.cpu().numpy() > 0).astype(np.uint8), unpack_vecs(d, f"{nb}_"))
+        C16 = E.count_dense(batch, a, k, basis, dtype=torch.uint16)
+        assert np.array_equal(C16.cpu().numpy().astype(np.int32), C.cpu().numpy())
+        # learn (learn.smk:306-357)
+        anns_o, M_o, nseq_o, tot_o, _ = O.learn_matrix(ids, C.cpu().numpy(), ann)
+        ann_index = {x: i for i, x in enumerate(anns_o)}
+        ann_id = np.array([ann_index.get(ann.get(O.accession(s), None), -1) for s in ids], dtype=np.int32)
+        M, totals = E.learn_dense(batch, a, k, basis, torch.from_numpy(ann_id), len(anns_o))
+        ref = csv_frame(d[f"{nb}_counts_csv"]).values.astype(np.int64)
+        assert np.array_equal(M[:-1].cpu().numpy(), ref[1:, 2:])
+        assert np.array_equal(totals.cpu().numpy(), ref[0, 2:])
+        assert np.array_equal(M[:-1].cpu().numpy(), M_o)
+        res_files[nb] = (ids, basis, C, anns_o, M[:-1].clone())
+    # apply (apply.smk:224-289): synB queries against the matrix learned on synA
+    idsB, basisB, CB, _, _ = res_files["synB"]
+    _, basisA, _, annsA, MA = res_files["synA"]
+    _, seqsB = read_fasta(os.path.join(GOLDEN, "synB.fasta"))
+    batchB = E.SequenceBatch.from_strings(seqsB)
+    QA = E.count_dense(batchB, a, k, basisA)                 # query counts over the learned columns
+    qn2 = E.row_norm2(CB)                                    # norm over the query file's own basis
+    r = E.apply_dense(QA, MA, qnorm2=qn2, full=True)
+    ref = d["apply_scores"]
+    got = r.scores.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) < 1e-12
+    i1, i2, s1, s2 = O.top2(got)
+    assert np.array_equal(r.top1.cpu().numpy(), i1) and np.array_equal(r.top2.cpu().numpy(), i2)
+    assert np.array_equal(r.score1.cpu().numpy(), s1) and np.array_equal(r.score2.cpu().numpy(), s2)
+    # predictions identical to the reference wherever its own top-2 gap is not a float tie
+    ri1, ri2, rs1, rs2 = O.top2(ref)
+    clear = (rs1 - rs2) > 1e-9
+    assert np.array_equal(r.top1.cpu().numpy()[clear], ri1[clear])
+    assert np.allclose(r.score1.cpu().numpy(), rs1, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("a,k,mf", [(5, 3, 0), (2, 8, 0), (0, 12, 2), (None, 3, 0), (1, 4, 5), ("ptm", 2, 0), (4, 9, 0)])
+def test_basis_and_dense_counts_random(a, k, mf):
+    rng = np.random.default_rng(hash((str(a), k)) % 2 ** 32)
+    seqs = _rand_seqs(rng, 700, 0, 900)
+    seqs[0] = ""
+    seqs[3] = "ACD"
+    batch = E.SequenceBatch.from_strings(seqs)
+    _, (si, pos, code, valid), (res, offs, lut, syms) = _codes_oracle(seqs, a, k)
+    want_basis, want_tot = O.basis_codes(si, pos, code, valid, mf)
+    basis = E.build_basis(batch, a, k, mf)
+    assert np.array_equal(basis.codes_host(), want_basis)
+    assert np.array_equal(basis.counts.cpu().numpy(), want_tot)
+    want = O.count_matrix(si, code, valid, len(seqs), want_basis)
+    got = E.count_dense(batch, a, k, basis).cpu().numpy()
+    assert np.array_equal(got, want)
+    if len(syms) ** k <= 20000:
+        ident = E.count_dense(batch, a, k, None).cpu().numpy()
+        full = O.count_matrix(si, code, valid, len(seqs), np.arange(len(syms) ** k, dtype=np.uint64))
+        assert np.array_equal(ident, full)
+
+
+def test_dense_counts_long_sequences_use_32bit_counters():
+    # > 65535 residues: the 16-bit shared-memory counters would overflow
+    seqs = ["A" * 70000, "ACDEFGHIKL" * 7000, "MKV"]
+    batch = E.SequenceBatch.from_strings(seqs)
+    got = E.count_dense(batch, 0, 2, None).cpu().numpy()
+    _, (si, pos, code, valid), _ = _codes_oracle(seqs, 0, 2)
+    want = O.count_matrix(si, code, valid, 3, np.arange(4, dtype=np.uint64))
+    assert np.array_equal(got, want) and got.max() == 69999
+    with pytest.raises(E.SkmError):
+        E.count_dense(batch, 0, 2, None, dtype=torch.uint16)
+
+
+@pytest.mark.parametrize("a,k", [(5, 3), (2, 8), (None, 5), (1, 6)])
+def test_count_csr(a, k):
+    rng = np.random.default_rng(k)
+    seqs = _rand_seqs(rng, 500, 0, 800)
+    seqs[7] = ""
+    batch = E.SequenceBatch.from_strings(seqs)
+    _, (si, pos, code, valid), (res, offs, lut, syms) = _codes_oracle(seqs, a, k)
+    rp, cc, cv = O.count_csr(si, code, valid, len(seqs))
+    rowptr, cols, vals = E.count_csr(batch, a, k, None)
+    assert np.array_equal(rowptr.cpu().numpy(), rp)
+    assert np.array_equal(cols.cpu().numpy().view(np.uint32).astype(np.uint64), cc)
+    assert np.array_equal(vals.cpu().numpy(), cv)
+    # over a filtered basis: columns instead of codes
+    basis = E.build_basis(batch, a, k, 1)
+    rowptr, cols, vals = E.count_csr(batch, a, k, basis)
+    dense = E.count_dense(batch, a, k, basis).cpu().numpy()
+    rp2 = rowptr.cpu().numpy()
+    for r in range(len(seqs)):
+        nz = np.flatnonzero(dense[r])
+        assert np.array_equal(cols.cpu().numpy()[rp2[r]:rp2[r + 1]], nz)
+        assert np.array_equal(vals.cpu().numpy()[rp2[r]:rp2[r + 1]], dense[r, nz])
+
+
+def test_learn_and_apply_random():
+    rng = np.random.default_rng(99)
+    seqs = _rand_seqs(rng, 3000, 0, 500)
+    a, k = 2, 5
+    batch = E.SequenceBatch.from_strings(seqs)
+    basis = E.build_basis(batch, a, k, 0)
+    n_ann = 37
+    ann_id = rng.integers(-1, n_ann, size=len(seqs)).astype(np.int32)
+    C = E.count_dense(batch, a, k, basis).cpu().numpy().astype(np.int64)
+    M, totals = E.learn_dense(batch, a, k, basis, torch.from_numpy(ann_id), n_ann)
+    want = np.zeros((n_ann + 1, basis.K), dtype=np.int64)
+    np.add.at(want, np.where(ann_id < 0, n_ann, ann_id), C)
+    assert np.array_equal(M.cpu().numpy(), want)
+    assert np.array_equal(totals.cpu().numpy(), C.sum(axis=0))
+    Q = torch.from_numpy(C[:777].astype(np.int32)).cuda()
+    r = E.apply_dense(Q, M[:-1].contiguous(), full=True, chunk=300)
+    S = O.cosine_scores(C[:777], want[:-1])
+    assert np.max(np.abs(r.scores.cpu().numpy() - S)) < 1e-12
+    i1, i2, s1, s2 = O.top2(r.scores.cpu().numpy())
+    assert np.array_equal(r.top1.cpu().numpy(), i1) and np.array_equal(r.top2.cpu().numpy(), i2)
+
+
+def test_apply_ties_and_zero_rows():
+    Q = torch.tensor([[0, 0, 0], [1, 1, 0], [2, 0, 0]], dtype=torch.int32).cuda()
+    M = torch.tensor([[1, 1, 0], [1, 1, 0], [0, 0, 0], [5, 0, 0]], dtype=torch.int64).cuda()
+    r = E.apply_dense(Q, M, full=True)
+    assert r.top1.tolist() == [0, 0, 3] and r.top2.tolist() == [1, 1, 0]
+    assert r.score1.tolist()[0] == 0.0 and abs(r.score1.tolist()[1] - 1.0) < 1e-15
+
+
+def test_errors_are_loud():
+    batch = E.SequenceBatch.from_strings(["ACD"])
+    with pytest.raises(E.SkmError):
+        E.encode_windows(batch, "ptm", 14)      # 30^14 > 2^64
+    with pytest.raises(E.SkmError):
+        E.build_basis(batch, None, 8)           # 20^8 > table limit
+    with pytest.raises(ValueError):
+        E.encode_windows(batch, "nope", 3)
