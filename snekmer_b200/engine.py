@@ -115,7 +115,7 @@ class SequenceBatch:
         # +16 bytes of slack keeps the buffer 16-byte granular; kernels never read past nres
         d_res = torch.empty(max(nres, 1) + 16, dtype=torch.uint8, device=dev)
         if nres:
-            src = torch.from_numpy(residues[:nres])
+            src = torch.from_numpy(residues[:nres] if residues.flags.writeable else residues[:nres].copy())
             d_res[:nres].copy_(src, non_blocking=pinned)
         d_off = torch.from_numpy(offsets).to(dev)
         return cls(d_res, d_off, offsets)
@@ -273,6 +273,18 @@ def basis_from_kmers(kmers: Sequence[str], alphabet: AlphabetT, k: int, device=N
     return Basis(tab.name, int(k), tab.symbols, d_codes, None, col, len(keep), S), keep
 
 
+def intersect_basis(target: Basis, other: Basis) -> Basis:
+    """Columns of `target`, restricted to codes that `other` also holds.
+
+    apply.smk:268-276 re-indexes query counts (columns = the query file's own
+    basis) onto the union of columns: a learned column receives a query count
+    only if the k-mer is in both bases."""
+    assert target.S == other.S
+    minus1 = torch.full_like(target.col_of_code, -1)
+    col = torch.where(other.col_of_code >= 0, target.col_of_code, minus1)
+    return Basis(target.alphabet, target.k, target.symbols, target.codes, target.counts, col, target.K, target.S)
+
+
 # ---------------------------------------------------------------------------
 # (b) counts
 # ---------------------------------------------------------------------------
@@ -373,7 +385,7 @@ def apply_dense(Q: torch.Tensor, M: torch.Tensor, qnorm2: Optional[torch.Tensor]
     s1 = torch.empty(nq, dtype=torch.float64, device=dev)
     s2 = torch.empty(nq, dtype=torch.float64, device=dev)
     scores = torch.empty((nq, A), dtype=torch.float64, device=dev) if full else None
-    chunk = max(1, min(chunk, nq))
+    chunk = max(1, min(chunk, nq, (1 << 31) // max(1, A * 8)))      # dots workspace <= 2 GiB
     ws_bytes = lib().skm_apply_dense_workspace(chunk, A, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for q0 in range(0, nq, chunk):

@@ -133,7 +133,10 @@ def test_golden_rule_fixtures(name):
     _, basisA, _, annsA, MA = res_files["synA"]
     _, seqsB = read_fasta(os.path.join(GOLDEN, "synB.fasta"))
     batchB = E.SequenceBatch.from_strings(seqsB)
-    QA = E.count_dense(batchB, a, k, basisA)                 # query counts over the learned columns
+    # query counts live on the query file's OWN basis (min_filter applies to it), re-indexed onto the
+    # learned columns: a k-mer contributes to the dot only if it is in both bases (apply.smk:268-276)
+    both = E.intersect_basis(basisA, basisB)
+    QA = E.count_dense(batchB, a, k, both)
     qn2 = E.row_norm2(CB)                                    # norm over the query file's own basis
     r = E.apply_dense(QA, MA, qnorm2=qn2, full=True)
     ref = d["apply_scores"]
