@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
+#include "skm_tile.cuh"
 
 namespace skm {
 
@@ -42,72 +43,89 @@ __device__ __forceinline__ void cta_seq_range(const int64_t *__restrict__ off, i
     if (i == 0) *lo = 0;
 }
 
-template <typename CodeT, int NW>
-__global__ void __launch_bounds__(256) basis_small_kernel(const uint8_t *__restrict__ res, int64_t nres,
-                                                          const int64_t *__restrict__ off, int64_t nseq,
-                                                          const uint8_t *__restrict__ lut, int nsym, int k, int S,
-                                                          uint64_t res_base, unsigned long long *__restrict__ g_count,
-                                                          unsigned long long *__restrict__ g_first) {
-    extern __shared__ __align__(16) uint32_t s_tab[];   // [S] counts, [S] relative first positions
+constexpr int BS_SEG = ts_seg_cap(52);              // residues per staged segment (52 per thread)
+constexpr int BS_SYM_BYTES = ts_sym_bytes(BS_SEG);
+
+// One kernel for both table kinds.  SMALL: per-CTA tables in shared memory ([S] counts, [S] first positions
+// relative to the CTA's residue range), merged into the global tables with S atomics per CTA.  !SMALL: the
+// tables are large and L2-resident; windows update them directly (low contention because S is large).
+template <bool SMALL>
+__global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__restrict__ res, int64_t nres,
+                                                           const int64_t *__restrict__ off, int64_t nseq,
+                                                           const uint8_t *__restrict__ lut, uint32_t nsym, int k,
+                                                           uint32_t pow_k1, int S, uint64_t res_base,
+                                                           unsigned long long *__restrict__ g_count,
+                                                           unsigned long long *__restrict__ g_first) {
+    extern __shared__ __align__(128) uint8_t s_raw[];   // symbol buffer, then (SMALL) the two tables
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_range[2];
-    __shared__ unsigned int s_next;
-    uint32_t *s_cnt = s_tab, *s_min = s_tab + S;
-    s_lut[threadIdx.x] = lut[threadIdx.x];
-    for (int i = threadIdx.x; i < S; i += blockDim.x) { s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }
-    if (threadIdx.x == 0) { cta_seq_range(off, nseq, &s_range[0], &s_range[1]); s_next = 0; }
+    __shared__ unsigned int s_nstart;
+    uint8_t *s_sym = s_raw;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw + BS_SYM_BYTES), *s_min = s_cnt + S;
+    const uint32_t sym_addr = smem_addr(s_sym), cnt_addr = smem_addr(s_cnt), min_addr = smem_addr(s_min);
+    const int tid = threadIdx.x;
+    ts_lut_init(s_lut, lut);
+    if (SMALL) for (int i = tid; i < S; i += blockDim.x) { s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }
+    if (tid == 0) { cta_seq_range(off, nseq, &s_range[0], &s_range[1]); s_nstart = 0; }
     __syncthreads();
     const int64_t lo = s_range[0], hi = s_range[1];
-    const int lane = threadIdx.x & 31;
-    if (lo < hi) {
-        const int64_t base = __ldg(off + lo);            // relative positions fit 32 bits (host sizes the grid)
-        for (;;) {
-            unsigned int t = 0;
-            if (lane == 0) t = atomicAdd(&s_next, 1u);
-            t = __shfl_sync(FULL, t, 0);
-            const int64_t s = lo + t;
-            if (s >= hi) break;
-            const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
-            warp_scan_sequence<CodeT, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t g, CodeT code, bool ok) {
-                if (ok) {
-                    atomicAdd(&s_cnt[code], 1u);
-                    const uint32_t rel = uint32_t(g - base);
-                    if (rel < s_min[code]) atomicMin(&s_min[code], rel);
-                }
-            });
-        }
+    if (lo >= hi) return;
+    const int64_t r_lo = __ldg(off + lo), r_hi = __ldg(off + hi);
+    int64_t cur = lo;                 // first sequence that starts at or after `a`
+    bool first = true;
+    uint32_t tail = 0;
+    for (int64_t a = r_lo; a < r_hi;) {
+        const int64_t b = min(r_hi, (a + BS_SEG) & ~int64_t(15));
+        if (!first) ts_tail_write(s_sym, tail, k);
+        const TsSeg g = ts_stage(res, nres, a, b, s_lut, s_sym);
         __syncthreads();
-        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        if (first) ts_invalidate_front(s_sym, g);
+        unsigned int mine = 0;
+        for (int64_t s = cur + tid; s < hi; s += blockDim.x) {
+            const int64_t o = __ldg(off + s);
+            if (o >= b) break;
+            s_sym[g.lo + int(o - a)] |= uint8_t(SYM_FLAG);
+            ++mine;
+        }
+        if (mine) atomicAdd(&s_nstart, mine);
+        __syncthreads();
+        cur += s_nstart;
+        const int C = ts_chunk(g.hi - g.lo);
+        const int i0 = g.lo + tid * C, i1 = min(i0 + C, g.hi);
+        // position of a window start relative to r_lo = shared address of its LAST symbol + to_rel
+        const int64_t to_rel64 = (g.base - r_lo) - TS_PAD - (k - 1) - int64_t(sym_addr);
+        const uint32_t to_rel = uint32_t(to_rel64);     // modular: the sum is in [0, 2^32)
+        ts_scan_chunk<uint32_t>(
+            sym_addr, i0, i1, k, nsym, pow_k1,
+            [&](uint32_t p, uint32_t code, bool ok) {
+                if (ok) {
+                    const uint32_t rel = p + to_rel;
+                    if (SMALL) {
+                        reds_add_u32(cnt_addr + (code << 2), 1u);
+                        if (rel < s_min[code]) reds_min_u32(min_addr + (code << 2), rel);
+                    } else {
+                        atomicAdd(g_count + code, 1ull);
+                        const unsigned long long pos = res_base + uint64_t(r_lo) + rel;
+                        // stale reads can only be too large (first is monotone decreasing): never skips a needed min
+                        if (pos < __ldcg(g_first + code)) atomicMin(g_first + code, pos);
+                    }
+                }
+            },
+            [](uint32_t) {});
+        tail = ts_tail_read(s_sym, g, k);
+        first = false;
+        a = b;
+        __syncthreads();
+        if (tid == 0) s_nstart = 0;    // ordered before the next atomicAdd by the barrier after staging
+    }
+    if (SMALL) {
+        for (int i = tid; i < S; i += blockDim.x) {
             const uint32_t c = s_cnt[i];
             if (c) {
                 atomicAdd(g_count + i, (unsigned long long)c);
-                atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(base) + s_min[i]));
+                atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + s_min[i]));
             }
         }
-    }
-}
-
-template <typename CodeT, int NW>
-__global__ void __launch_bounds__(256) basis_large_kernel(const uint8_t *__restrict__ res, int64_t nres,
-                                                          const int64_t *__restrict__ off, int64_t nseq,
-                                                          const uint8_t *__restrict__ lut, int nsym, int k,
-                                                          uint64_t res_base, unsigned long long *__restrict__ g_count,
-                                                          unsigned long long *__restrict__ g_first) {
-    __shared__ uint8_t s_lut[256];
-    s_lut[threadIdx.x] = lut[threadIdx.x];
-    __syncthreads();
-    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t s = warp; s < nseq; s += nwarps) {
-        const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
-        warp_scan_sequence<CodeT, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t g, CodeT code, bool ok) {
-            if (ok) {
-                atomicAdd(g_count + code, 1ull);
-                const unsigned long long pos = res_base + uint64_t(g);
-                // stale reads can only be too large (first is monotone decreasing): never skips a needed min
-                if (pos < __ldcg(g_first + code)) atomicMin(g_first + code, pos);
-            }
-        });
     }
 }
 
@@ -170,24 +188,30 @@ int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres, const int64_t 
     }
     if (!d_count || !d_first) { set_error("skm_basis_accumulate: NULL table"); return SKM_ERR_INVALID; }
     if (nseq == 0 || nres == 0) return SKM_OK;
+    if (!ts_supported(nsym, k)) { set_error("skm_basis_accumulate: nsym=%d k=%d outside the kernel envelope (nsym <= %d, k <= %d)", nsym, k, TS_MAX_NSYM, TS_MAX_K); return SKM_ERR_UNSUPPORTED; }
     const int64_t S = (int64_t)S128;
     cudaStream_t st = (cudaStream_t)stream;
-    const int nw = neighbour_words(k);
     auto *cnt = reinterpret_cast<unsigned long long *>(d_count);
     auto *fst = reinterpret_cast<unsigned long long *>(d_first);
-    if (S <= SMALL_S) {
-        const size_t smem = size_t(S) * 8;
-        int64_t grid = int64_t(sm_count()) * (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
-        const int64_t min_grid = (nres >> 30) + 1;       // keep each CTA's residue range well below 2^32
-        if (grid < min_grid) grid = min_grid;
-        SKM_DISPATCH_NW(nw, {
-            auto kern = basis_small_kernel<uint32_t, NW>;
-            SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(unsigned)grid, 256, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, (int)S, res_base, cnt, fst);
-        });
+    uint32_t pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
+    const bool small = S <= SMALL_S;
+    const size_t smem = size_t(BS_SYM_BYTES) + (small ? size_t(S) * 8 : 0);
+    int per_sm = int((227 * 1024) / (smem + 1536));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = int64_t(sm_count()) * per_sm;
+    const int64_t min_grid = (nres >> 30) + 1;           // keep each CTA's residue range well below 2^32
+    if (grid < min_grid) grid = min_grid;
+    const int64_t max_grid = (nres + BS_SEG - 1) / BS_SEG;   // no point in CTAs with less than a segment
+    if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
+    if (small) {
+        auto kern = basis_kernel<true>;
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst);
     } else {
-        const int grid = sm_count() * 8;
-        SKM_DISPATCH_NW(nw, (basis_large_kernel<uint32_t, NW><<<grid, 256, 0, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, res_base, cnt, fst)));
+        auto kern = basis_kernel<false>;
+        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst);
     }
     SKM_LAUNCH_CHECK("basis_accumulate");
     return SKM_OK;

@@ -18,92 +18,115 @@
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
+#include "skm_tile.cuh"
 
 namespace skm {
 
 // ---------------------------------------------------------------------------
 // dense
 // ---------------------------------------------------------------------------
-template <typename CntT> struct cnt_ops;
+constexpr int CD_MAX_ROWS = 32;   // rows (sequences) per tile
+
+// counters live in shared memory in the OUTPUT layout (int32, or uint16 packed two per word), so a tile
+// is flushed with one bulk shared->global copy
+template <typename OutT> struct cnt_ops;
+template <> struct cnt_ops<int32_t> {
+    static __device__ __forceinline__ void add(uint32_t base, uint32_t idx) { reds_add_u32(base + (idx << 2), 1u); }
+};
 template <> struct cnt_ops<uint16_t> {
-    // two 16-bit counters per 32-bit word; no carry while a count stays < 65536
-    static __device__ __forceinline__ void add(uint32_t *words, uint32_t idx) {
-        atomicAdd(words + (idx >> 1), 1u << ((idx & 1u) * 16u));
+    // no carry into the upper half while a count stays < 65536 (host: max_len <= 65535)
+    static __device__ __forceinline__ void add(uint32_t base, uint32_t idx) {
+        reds_add_u32(base + ((idx >> 1) << 2), 1u << ((idx & 1u) << 4));
     }
 };
-template <> struct cnt_ops<uint32_t> {
-    static __device__ __forceinline__ void add(uint32_t *words, uint32_t idx) { atomicAdd(words + idx, 1u); }
-};
 
-template <typename CntT, typename OutT>
-__device__ __forceinline__ void flush_tile(uint32_t *s_words, OutT *__restrict__ out, int64_t n_elems) {
-    // s_words holds n_elems counters of CntT, out is the contiguous destination (element 0 of the tile).
-    CntT *s_cnt = reinterpret_cast<CntT *>(s_words);
-    constexpr int VEC = 16 / sizeof(OutT);          // output elements per 16-byte store
-    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    if (aligned) {
-        const int64_t nvec = n_elems / VEC;
-        for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
-            OutT tmp[VEC];
-            if constexpr (sizeof(CntT) == 2 && VEC == 4) {
-                const uint2 c = *reinterpret_cast<const uint2 *>(s_cnt + v * 4);
-                *reinterpret_cast<uint2 *>(s_cnt + v * 4) = make_uint2(0u, 0u);
-                tmp[0] = OutT(c.x & 0xFFFFu); tmp[1] = OutT(c.x >> 16);
-                tmp[2] = OutT(c.y & 0xFFFFu); tmp[3] = OutT(c.y >> 16);
-            } else if constexpr (sizeof(CntT) == 2 && VEC == 8) {
-                const uint4 c = *reinterpret_cast<const uint4 *>(s_cnt + v * 8);
-                *reinterpret_cast<uint4 *>(s_cnt + v * 8) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4 *>(tmp) = c;
-            } else {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) { tmp[j] = OutT(s_cnt[v * VEC + j]); s_cnt[v * VEC + j] = 0; }
-            }
-            __stcs(reinterpret_cast<uint4 *>(out) + v, *reinterpret_cast<const uint4 *>(tmp));
-        }
-        for (int64_t i = nvec * VEC + threadIdx.x; i < n_elems; i += blockDim.x) { out[i] = OutT(s_cnt[i]); s_cnt[i] = 0; }
-    } else {
-        for (int64_t i = threadIdx.x; i < n_elems; i += blockDim.x) { out[i] = OutT(s_cnt[i]); s_cnt[i] = 0; }
-    }
-}
-
-template <typename CodeT, int NW, typename CntT, typename OutT>
-__global__ void __launch_bounds__(256) count_dense_kernel(const uint8_t *__restrict__ res, int64_t nres,
-                                                          const int64_t *__restrict__ off, int64_t nseq,
-                                                          const uint8_t *__restrict__ lut, int nsym, int k,
-                                                          const int32_t *__restrict__ col_of_code, int K, int T,
-                                                          OutT *__restrict__ out) {
-    extern __shared__ __align__(16) uint32_t s_words[];   // T*K counters of CntT (rounded up to 16 B)
+// smem: [T*K counters of OutT | symbol buffer for seg_cap residues]
+template <typename OutT, bool HAS_MAP>
+__global__ void __launch_bounds__(TS_THREADS) count_dense_kernel(const uint8_t *__restrict__ res, int64_t nres,
+                                                                 const int64_t *__restrict__ off, int64_t nseq,
+                                                                 const uint8_t *__restrict__ lut, uint32_t nsym, int k,
+                                                                 uint32_t pow_k1, const int32_t *__restrict__ col_of_code,
+                                                                 int K, int T, int seg_cap, OutT *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ uint8_t s_lut[256];
-    __shared__ unsigned int s_next;
-    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __shared__ int32_t s_off[CD_MAX_ROWS + 1];        // row starts relative to the tile
     const int64_t tile_elems = int64_t(T) * K;
-    const int n_words = int((tile_elems * sizeof(CntT) + 3) / 4);
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_words[i] = 0;
-    if (threadIdx.x == 0) s_next = 0;
+    const uint32_t cnt_bytes = uint32_t((size_t(tile_elems) * sizeof(OutT) + 15) & ~size_t(15));
+    uint4 *s_cnt4 = reinterpret_cast<uint4 *>(s_raw);
+    uint8_t *s_sym = s_raw + cnt_bytes;
+    const uint32_t cnt_addr = smem_addr(s_raw), sym_addr = smem_addr(s_sym);
+    ts_lut_init(s_lut, lut);
+    for (int i = threadIdx.x; i < int(cnt_bytes >> 4); i += blockDim.x) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
     const int64_t ntiles = (nseq + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t s0 = tile * T;
         const int rows = (nseq - s0 < T) ? int(nseq - s0) : T;
-        for (;;) {
-            unsigned int r = 0;
-            if (lane == 0) r = atomicAdd(&s_next, 1u);
-            r = __shfl_sync(FULL, r, 0);
-            if (r >= (unsigned)rows) break;
-            const int64_t b = __ldg(off + s0 + r), e = __ldg(off + s0 + r + 1);
-            const uint32_t row_base = r * uint32_t(K);
-            warp_scan_sequence<CodeT, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t, CodeT code, bool ok) {
-                if (ok) {
-                    const int32_t col = col_of_code ? __ldg(col_of_code + code) : int32_t(code);
-                    if (col >= 0) cnt_ops<CntT>::add(s_words, row_base + uint32_t(col));
+        const int64_t r0 = __ldg(off + s0), r1 = __ldg(off + s0 + rows);
+        for (int r = tid; r <= rows; r += blockDim.x) s_off[r] = int32_t(__ldg(off + s0 + r) - r0);
+        bool first = true;
+        uint32_t tail = 0;
+        for (int64_t a = r0; a < r1;) {
+            const int64_t b = min(r1, (a + seg_cap) & ~int64_t(15));
+            if (!first) ts_tail_write(s_sym, tail, k);
+            const TsSeg g = ts_stage(res, nres, a, b, s_lut, s_sym);
+            __syncthreads();
+            if (first) ts_invalidate_front(s_sym, g);
+            const int a_rel = int(a - r0), b_rel = int(b - r0);
+            for (int r = tid; r < rows; r += blockDim.x) {
+                const int o = s_off[r];
+                if (o >= a_rel && o < b_rel) s_sym[g.lo + (o - a_rel)] |= uint8_t(SYM_FLAG);
+            }
+            __syncthreads();
+            const int C = ts_chunk(g.hi - g.lo);
+            const int i0 = g.lo + tid * C, i1 = min(i0 + C, g.hi);
+            if (i0 < i1) {
+                const int shift = a_rel - g.lo;                 // tile-relative position = symbol index + shift
+                const int rel0 = i0 + shift;
+                int lo = 0, hi = rows;                          // rows that start strictly before rel0
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] < rel0) lo = mid + 1; else hi = mid;
                 }
-            });
+                int row = lo - 1;                               // -1 only when i0 is the (flagged) tile start
+                uint32_t row_base = uint32_t(row) * uint32_t(K);
+                const int shift_addr = shift - int(sym_addr);   // tile-relative position = shared address + shift_addr
+                ts_scan_chunk<uint32_t>(
+                    sym_addr, i0, i1, k, nsym, pow_k1,
+                    [&](uint32_t, uint32_t code, bool ok) {
+                        int32_t col = -1;
+                        if (ok) col = HAS_MAP ? __ldg(col_of_code + code) : int32_t(code);
+                        if (col >= 0) cnt_ops<OutT>::add(cnt_addr, row_base + uint32_t(col));
+                    },
+                    [&](uint32_t p) {
+                        const int rel = int(p) + shift_addr;
+                        do { ++row; } while (s_off[row + 1] <= rel);   // skips empty sequences; s_off[rows] > rel
+                        row_base = uint32_t(row) * uint32_t(K);
+                    });
+            }
+            tail = ts_tail_read(s_sym, g, k);
+            first = false;
+            a = b;
+            __syncthreads();
+        }
+        // ---- flush: the tile is one contiguous range of the [N, K] output ----
+        ts_bulk_fence();
+        __syncthreads();
+        OutT *dst = out + s0 * K;
+        const int64_t n_elems = int64_t(rows) * K;
+        const OutT *s_cnt = reinterpret_cast<const OutT *>(s_raw);
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            const uint32_t bytes = uint32_t(n_elems * sizeof(OutT)) & ~15u;
+            if (tid == 0 && bytes) ts_bulk_store(dst, cnt_addr, bytes);
+            for (int64_t i = bytes / sizeof(OutT) + tid; i < n_elems; i += blockDim.x) dst[i] = s_cnt[i];
+            if (tid == 0) ts_bulk_wait_read();
+        } else {
+            for (int64_t i = tid; i < n_elems; i += blockDim.x) dst[i] = s_cnt[i];
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_next = 0;
-        flush_tile<CntT, OutT>(s_words, out + s0 * K, int64_t(rows) * K);
-        __syncthreads();
+        for (int i = tid; i < int(cnt_bytes >> 4); i += blockDim.x) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+        // the next tile touches the counters only after two more barriers
     }
 }
 
@@ -194,34 +217,44 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
     if (out_bits == 16 && (max_len <= 0 || max_len > 65535)) { set_error("skm_count_dense: uint16 output needs 0 < max_len <= 65535"); return SKM_ERR_INVALID; }
     if (nseq == 0 || K == 0) return SKM_OK;
     if (!d_counts) { set_error("skm_count_dense: d_counts is NULL"); return SKM_ERR_INVALID; }
-    const bool cnt16 = (max_len > 0 && max_len <= 65535);
-    const size_t cnt_bytes = cnt16 ? 2 : 4;
+    if (!ts_supported(nsym, k)) { set_error("skm_count_dense: nsym=%d k=%d outside the kernel envelope (nsym <= %d, k <= %d)", nsym, k, TS_MAX_NSYM, TS_MAX_K); return SKM_ERR_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(d_counts) & 15u) != 0) { set_error("skm_count_dense: d_counts must be 16-byte aligned"); return SKM_ERR_INVALID; }
+    const size_t out_bytes = out_bits / 8;
     const size_t smem_cap = 200 * 1024;
-    if (size_t(K) * cnt_bytes > smem_cap) {
+    if (size_t(K) * out_bytes > smem_cap) {
         set_error("skm_count_dense: K=%lld rows do not fit shared memory; use skm_count_csr", (long long)K);
         return SKM_ERR_UNSUPPORTED;
     }
-    // tile: as many rows as fit ~64 KB (3 CTAs/SM), multiple of 8 so every tile start is 16-byte aligned
-    int64_t T = int64_t(64 * 1024 / (size_t(K) * cnt_bytes));
-    if (T >= 8) T &= ~int64_t(7);
+    // tile: as many rows as keep 3 CTAs per SM (a multiple of 4 int32 / 8 uint16 rows, so every tile start is
+    // 16-byte aligned and goes out as one bulk copy), at most 32; the symbol buffer holds a typical tile in
+    // one segment (28 residues per thread)
+    const int seg_cap = ts_seg_cap(28);
+    const size_t sym_bytes = (size_t)ts_sym_bytes(seg_cap);
+    const size_t sm_bytes = 227 * 1024, per_cta_reserved = 1024 + 512;
+    const size_t budget = sm_bytes / 3 - per_cta_reserved - sym_bytes - 16;
+    int64_t T = int64_t(budget / (size_t(K) * out_bytes));
+    const int64_t align_rows = 16 / (int64_t)out_bytes;
+    if (T >= align_rows) T -= T % align_rows;
     if (T < 1) T = 1;
-    if (T > 64) T = 64;
-    const size_t smem = ((size_t(T) * K * cnt_bytes + 15) / 16) * 16;
+    if (T > CD_MAX_ROWS) T = CD_MAX_ROWS;
+    const size_t smem = ((size_t(T) * K * out_bytes + 15) & ~size_t(15)) + sym_bytes;
     const int64_t ntiles = (nseq + T - 1) / T;
-    const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    int per_sm = int(sm_bytes / (smem + per_cta_reserved));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
     const int grid = (int)std::min<int64_t>(ntiles, int64_t(sm_count()) * per_sm);
     cudaStream_t st = (cudaStream_t)stream;
-    const int nw = neighbour_words(k);
-#define SKM_LAUNCH_DENSE(CNT, OUT)                                                                                   \
-    SKM_DISPATCH_NW(nw, {                                                                                            \
-        auto kern = count_dense_kernel<uint32_t, NW, CNT, OUT>;                                                      \
+    uint32_t pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
+#define SKM_LAUNCH_DENSE(OUT, MAP)                                                                                   \
+    {                                                                                                                \
+        auto kern = count_dense_kernel<OUT, MAP>;                                                                    \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-        kern<<<grid, 256, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, (int)K,      \
-                                      (int)T, (OUT *)d_counts);                                                      \
-    })
-    if (cnt16 && out_bits == 32) { SKM_LAUNCH_DENSE(uint16_t, int32_t); }
-    else if (cnt16 && out_bits == 16) { SKM_LAUNCH_DENSE(uint16_t, uint16_t); }
-    else { SKM_LAUNCH_DENSE(uint32_t, int32_t); }
+        kern<<<grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1,    \
+                                             d_col_of_code, (int)K, (int)T, seg_cap, (OUT *)d_counts);               \
+    }
+    if (out_bits == 32) { if (d_col_of_code) SKM_LAUNCH_DENSE(int32_t, true) else SKM_LAUNCH_DENSE(int32_t, false) }
+    else { if (d_col_of_code) SKM_LAUNCH_DENSE(uint16_t, true) else SKM_LAUNCH_DENSE(uint16_t, false) }
 #undef SKM_LAUNCH_DENSE
     SKM_LAUNCH_CHECK("count_dense_kernel");
     return SKM_OK;
