@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
     __shared__ unsigned int s_nstart;
     uint8_t *s_sym = s_raw;
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw + BS_SYM_BYTES), *s_min = s_cnt + S;
-    const uint32_t sym_addr = smem_addr(s_sym), cnt_addr = smem_addr(s_cnt), min_addr = smem_addr(s_min);
+    uint32_t sym_addr = smem_addr(s_sym), cnt_addr = smem_addr(s_cnt), min_addr = smem_addr(s_min);
+    asm volatile("" : "+r"(sym_addr), "+r"(cnt_addr), "+r"(min_addr));   // keep the window addresses in registers
     const int tid = threadIdx.x;
     ts_lut_init(s_lut, lut);
     if (SMALL) for (int i = tid; i < S; i += blockDim.x) { s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }

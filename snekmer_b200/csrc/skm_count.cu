@@ -15,6 +15,8 @@
 //
 // Sparse path (skm_count_csr): window codes -> columns, segmented radix sort of
 // each sequence's keys, run-length encode into CSR.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(TS_THREADS) count_dense_kernel(const uint8_t *
     const uint32_t cnt_bytes = uint32_t((size_t(tile_elems) * sizeof(OutT) + 15) & ~size_t(15));
     uint4 *s_cnt4 = reinterpret_cast<uint4 *>(s_raw);
     uint8_t *s_sym = s_raw + cnt_bytes;
-    const uint32_t cnt_addr = smem_addr(s_raw), sym_addr = smem_addr(s_sym);
+    uint32_t cnt_addr = smem_addr(s_raw), sym_addr = smem_addr(s_sym);
+    asm volatile("" : "+r"(cnt_addr), "+r"(sym_addr));      // keep the window addresses in registers
     ts_lut_init(s_lut, lut);
     for (int i = threadIdx.x; i < int(cnt_bytes >> 4); i += blockDim.x) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -225,22 +228,26 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         set_error("skm_count_dense: K=%lld rows do not fit shared memory; use skm_count_csr", (long long)K);
         return SKM_ERR_UNSUPPORTED;
     }
-    // tile: as many rows as keep 3 CTAs per SM (a multiple of 4 int32 / 8 uint16 rows, so every tile start is
-    // 16-byte aligned and goes out as one bulk copy), at most 32; the symbol buffer holds a typical tile in
-    // one segment (28 residues per thread)
-    const int seg_cap = ts_seg_cap(28);
+    // Tile shape.  Many small CTAs per SM (each with its own tile in flight) hide the staging-load, barrier
+    // and bulk-store latencies of one another: 128 threads, ~16 KB of counters, rows a multiple of
+    // 4 (int32) / 8 (uint16) so that every tile start is 16-byte aligned and leaves as one bulk copy.
+    int64_t align_rows = 16 / (int64_t)out_bytes;           // rows per 16 bytes of output in the worst case ...
+    while (align_rows > 1 && (size_t(align_rows / 2) * K * out_bytes) % 16 == 0) align_rows /= 2;   // ... fewer when K allows
+    int threads = 128;
+    int64_t T = int64_t((16 * 1024) / (size_t(K) * out_bytes));
+    if (const char *e = getenv("SKM_CD_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
+    if (const char *e = getenv("SKM_CD_ROWS")) { const int v = atoi(e); if (v > 0) T = v; }
+    if (T >= align_rows) T -= T % align_rows;
+    if (T < align_rows) T = (size_t(align_rows) * K * out_bytes <= 64 * 1024) ? align_rows : 1;
+    if (T > CD_MAX_ROWS) T = CD_MAX_ROWS;
+    const int seg_cap = ts_seg_cap(28, threads);
     const size_t sym_bytes = (size_t)ts_sym_bytes(seg_cap);
     const size_t sm_bytes = 227 * 1024, per_cta_reserved = 1024 + 512;
-    const size_t budget = sm_bytes / 3 - per_cta_reserved - sym_bytes - 16;
-    int64_t T = int64_t(budget / (size_t(K) * out_bytes));
-    const int64_t align_rows = 16 / (int64_t)out_bytes;
-    if (T >= align_rows) T -= T % align_rows;
-    if (T < 1) T = 1;
-    if (T > CD_MAX_ROWS) T = CD_MAX_ROWS;
     const size_t smem = ((size_t(T) * K * out_bytes + 15) & ~size_t(15)) + sym_bytes;
     const int64_t ntiles = (nseq + T - 1) / T;
     int per_sm = int(sm_bytes / (smem + per_cta_reserved));
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
     const int grid = (int)std::min<int64_t>(ntiles, int64_t(sm_count()) * per_sm);
     cudaStream_t st = (cudaStream_t)stream;
@@ -250,7 +257,7 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
     {                                                                                                                \
         auto kern = count_dense_kernel<OUT, MAP>;                                                                    \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-        kern<<<grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1,    \
+        kern<<<grid, threads, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1,       \
                                              d_col_of_code, (int)K, (int)T, seg_cap, (OUT *)d_counts);               \
     }
     if (out_bits == 32) { if (d_col_of_code) SKM_LAUNCH_DENSE(int32_t, true) else SKM_LAUNCH_DENSE(int32_t, false) }

@@ -27,7 +27,7 @@
 
 namespace skm {
 
-constexpr int TS_THREADS = 256;
+constexpr int TS_THREADS = 256;                    // upper bound of the CTA size of scanner kernels
 constexpr int TS_PAD = 64;                         // >= k-1 halo symbols in front of the segment
 constexpr int TS_MAX_K = TS_PAD;                   // k-1 <= 63
 constexpr int TS_MAX_NSYM = 64;                    // digits are 6 bits
@@ -35,12 +35,12 @@ constexpr uint32_t SYM_BAD = 0x40u, SYM_FLAG = 0x80u, SYM_DIGIT = 0x3Fu;
 
 // shared bytes of a symbol buffer that stages up to seg_cap residues (seg_cap % 16 == 0)
 __host__ __device__ constexpr int ts_sym_bytes(int seg_cap) { return TS_PAD + seg_cap + 32; }
-// segment capacity when every thread owns at most c residues (c = 4 * odd)
-__host__ __device__ constexpr int ts_seg_cap(int c) { return TS_THREADS * c; }
+// segment capacity when every one of `threads` threads owns at most c residues (c = 4 * odd)
+__host__ __device__ constexpr int ts_seg_cap(int c, int threads = TS_THREADS) { return threads * c; }
 
-// chunk length for n positions over TS_THREADS threads: smallest 4*odd >= ceil(n / threads)
+// chunk length for n positions over the CTA's threads: smallest 4*odd >= ceil(n / threads)
 __device__ __forceinline__ int ts_chunk(int n) {
-    int c = (n + TS_THREADS - 1) / TS_THREADS;
+    int c = (n + int(blockDim.x) - 1) / int(blockDim.x);
     c = (c + 3) >> 2;            // words
     c |= 1;                      // odd
     return c << 2;
