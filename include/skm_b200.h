@@ -177,6 +177,21 @@ SKM_API int skm_row_norm2_i32(const int32_t *d_X, int64_t rows, int64_t cols,
 SKM_API int skm_row_norm2_i64(const int64_t *d_X, int64_t rows, int64_t cols,
                       double *d_out, skm_stream_t stream);
 
+/* KmerBasis.transform / KmerVec.harmonize, vectorize.py:54-119,330-345: column gather with
+ * zero fill.  out[r, j] = in[r, idx[j]] (row-major [rows, n] -> [rows, p]); idx[j] outside
+ * [0, n) gives a zero column.  elem_bytes in {1, 2, 4, 8}. */
+SKM_API int skm_gather_columns(const void *d_in, int64_t rows, int64_t n, int elem_bytes,
+                       const int64_t *d_idx, int64_t p, void *d_out,
+                       skm_stream_t stream);
+
+/* Merge.merge_dataframes / merge_with_base, learn.smk:467-494,556-579: outer join of count
+ * matrices on their k-mer columns and row-wise sum.  dst[row_map[r], col_map[c]] +=
+ * src[r, c] for int64 matrices; negative map entries drop the row / column. */
+SKM_API int skm_scatter_add_i64(const int64_t *d_src, int64_t rows, int64_t cols,
+                        const int64_t *d_row_map, const int64_t *d_col_map,
+                        int64_t *d_dst, int64_t dst_rows, int64_t dst_cols,
+                        skm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

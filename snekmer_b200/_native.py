@@ -53,6 +53,8 @@ SIGNATURES = {
     "skm_apply_dense": (_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_row_norm2_i32": (_int, [_p, _i64, _i64, _p, _p]),
     "skm_row_norm2_i64": (_int, [_p, _i64, _i64, _p, _p]),
+    "skm_gather_columns": (_int, [_p, _i64, _i64, _int, _p, _i64, _p, _p]),
+    "skm_scatter_add_i64": (_int, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _p]),
 }
 
 

@@ -59,7 +59,11 @@ class AlphabetTables:
 _tables_cache = {}
 
 
-def alphabet_tables(alphabet: AlphabetT, device=None) -> AlphabetTables:
+def alphabet_tables(alphabet, device=None) -> AlphabetTables:
+    """Device tables of an alphabet given by name / index / None — or an AlphabetTables
+    object, which is passed through (lets callers use ad-hoc symbol sets)."""
+    if isinstance(alphabet, AlphabetTables):
+        return alphabet
     dev = _require_cuda(device)
     name = _alphabet.get_alphabet_name(alphabet)
     key = (name, dev.index, tuple(sorted(_alphabet.residue_map(name).items())))
@@ -73,6 +77,26 @@ def alphabet_tables(alphabet: AlphabetT, device=None) -> AlphabetTables:
         lut=torch.frombuffer(bytearray(lut_host), dtype=torch.uint8).to(dev),
         charmap=torch.frombuffer(bytearray(_alphabet.charmap(name)), dtype=torch.uint8).to(dev),
     )
+    _tables_cache[key] = t
+    return t
+
+
+def alphabet_tables_from_symbols(symbols: str, device=None) -> AlphabetTables:
+    """Identity alphabet over already REDUCED text: every character of `symbols` is its own
+    symbol, everything else is invalid.  This is what the learn / apply rules need: they
+    count windows of the reduced strings stored in the .npz against a k-mer list
+    (learn.smk:359-383, apply.smk:188-206), so a window can only match when all its
+    characters occur in that list."""
+    dev = _require_cuda(device)
+    syms = "".join(sorted(set(symbols)))
+    key = ("=" + syms, dev.index)
+    hit = _tables_cache.get(key)
+    if hit is not None:
+        return hit
+    lut_host = _native.lut_build(syms, syms, syms)
+    t = AlphabetTables(name="=" + syms, symbols=syms, nsym=len(syms), lut_host=lut_host,
+                       lut=torch.frombuffer(bytearray(lut_host), dtype=torch.uint8).to(dev),
+                       charmap=torch.arange(256, dtype=torch.uint8, device=dev))
     _tables_cache[key] = t
     return t
 
@@ -273,6 +297,57 @@ def basis_from_kmers(kmers: Sequence[str], alphabet: AlphabetT, k: int, device=N
     return Basis(tab.name, int(k), tab.symbols, d_codes, None, col, len(keep), S), keep
 
 
+def gather_columns(matrix, index) -> "np.ndarray | torch.Tensor":
+    """out[:, j] = matrix[:, index[j]], zero where index[j] is outside [0, n) — the column
+    gather of KmerBasis.transform (vectorize.py:54-119).  numpy in → numpy out, tensor in → tensor out."""
+    as_numpy = not isinstance(matrix, torch.Tensor)
+    dev = _require_cuda(None if as_numpy else matrix.device)
+    if as_numpy:
+        arr = np.ascontiguousarray(matrix)
+        if arr.ndim == 1:
+            arr = arr.reshape(1, -1)
+        if arr.dtype.itemsize not in (1, 2, 4, 8) or arr.dtype.kind not in "iufb":
+            raise TypeError(f"gather_columns: unsupported dtype {arr.dtype}")
+        d_in = torch.from_numpy(arr.view(f"u{arr.dtype.itemsize}").view(np.dtype(f"i{arr.dtype.itemsize}"))).to(dev)
+    else:
+        d_in = matrix.contiguous()
+    rows, n = d_in.shape
+    idx = torch.as_tensor(np.asarray(index, dtype=np.int64) if not isinstance(index, torch.Tensor) else index,
+                          dtype=torch.int64, device=dev).contiguous()
+    out = torch.empty((rows, idx.numel()), dtype=d_in.dtype, device=dev)
+    check(lib().skm_gather_columns(_ptr(d_in), rows, n, d_in.element_size(), _ptr(idx), idx.numel(), _ptr(out), _stream()))
+    if as_numpy:
+        return out.cpu().numpy().view(arr.dtype)
+    return out
+
+
+def scatter_add(dst: torch.Tensor, src: torch.Tensor, row_map, col_map) -> None:
+    """dst[row_map[r], col_map[c]] += src[r, c] for int64 matrices (negative map entries are dropped):
+    the outer-join-and-sum of Merge.merge_dataframes (learn.smk:467-494)."""
+    dev = dst.device
+    assert dst.dtype == torch.int64 and src.dtype == torch.int64 and dst.is_contiguous()
+    src = src.contiguous()
+    rm = torch.as_tensor(row_map, dtype=torch.int64, device=dev).contiguous()
+    cm = torch.as_tensor(col_map, dtype=torch.int64, device=dev).contiguous()
+    assert rm.numel() == src.shape[0] and cm.numel() == src.shape[1]
+    check(lib().skm_scatter_add_i64(_ptr(src), src.shape[0], src.shape[1], _ptr(rm), _ptr(cm), _ptr(dst), dst.shape[0],
+                                    dst.shape[1], _stream()))
+
+
+def basis_from_codes(codes: np.ndarray, alphabet, k: int, device=None) -> Tuple[Basis, np.ndarray]:
+    """Basis whose column j holds code codes[j] (uint64, distinct)."""
+    dev = _require_cuda(device)
+    tab = alphabet_tables(alphabet, dev)
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    d_codes = torch.from_numpy(codes.view(np.int64)).to(dev)
+    col = torch.empty(S, dtype=torch.int32, device=dev)
+    check(lib().skm_basis_colmap(_ptr(d_codes), len(codes), S, _ptr(col), _stream()))
+    return Basis(tab.name, int(k), tab.symbols, d_codes, None, col, len(codes), S), np.arange(len(codes))
+
+
 def intersect_basis(target: Basis, other: Basis) -> Basis:
     """Columns of `target`, restricted to codes that `other` also holds.
 
@@ -303,6 +378,25 @@ def count_dense(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Option
                                 int(k), None if basis is None else _ptr(basis.col_of_code), S, K, bits, _ptr(out),
                                 batch.max_len, _stream()))
     return out
+
+
+def count_over_kmers(batch: SequenceBatch, alphabet, k: int, kmerlist: Sequence[str], dtype: torch.dtype = torch.int32) -> torch.Tensor:
+    """Counts [N, len(kmerlist)] with one column per LIST ENTRY, in list order
+    (``[k_counts.get(kmer, 0) for kmer in kmerlist]``, learn.smk:377-382): entries that
+    cannot be encoded (wrong length, foreign characters) are zero columns, repeated
+    entries repeat the column."""
+    basis, keep = basis_from_kmers(kmerlist, alphabet, k, batch.device)
+    n_list = len(kmerlist)
+    codes = basis.codes_host()
+    if basis.K == n_list and np.unique(codes).size == n_list:
+        return count_dense(batch, alphabet, k, basis, dtype=dtype)
+    # distinct codes -> dense columns, then expand to the list
+    uniq, inverse = np.unique(codes, return_inverse=True)
+    ub, _ = basis_from_codes(uniq, alphabet, k, batch.device)
+    C = count_dense(batch, alphabet, k, ub, dtype=dtype)
+    index = np.full(n_list, -1, dtype=np.int64)
+    index[keep] = inverse
+    return gather_columns(C, index)
 
 
 def count_csr(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis] = None):
@@ -343,6 +437,26 @@ def learn_dense(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Option
                                 int(k), None if basis is None else _ptr(basis.col_of_code), S, K, _ptr(ann_id),
                                 _ptr(order), int(n_ann), _ptr(M), _ptr(totals), _stream()))
     return M, totals
+
+
+def learn_over_kmers(batch: SequenceBatch, alphabet, k: int, kmerlist: Sequence[str], ann_id: torch.Tensor,
+                     n_ann: int) -> Tuple[np.ndarray, np.ndarray]:
+    """learn_dense over a k-mer LIST: (M int64 [n_ann, len(kmerlist)], totals int64 [len(kmerlist)]) on the
+    host, one column per list entry (zero columns for entries no window can match)."""
+    basis, keep = basis_from_kmers(kmerlist, alphabet, k, batch.device)
+    codes = basis.codes_host()
+    n_list = len(kmerlist)
+    plain = basis.K == n_list and np.unique(codes).size == n_list
+    if not plain:
+        uniq, inverse = np.unique(codes, return_inverse=True)
+        basis, _ = basis_from_codes(uniq, alphabet, k, batch.device)
+    M, totals = learn_dense(batch, alphabet, k, basis, ann_id, n_ann)
+    if not plain:
+        index = np.full(n_list, -1, dtype=np.int64)
+        index[keep] = inverse
+        M = gather_columns(M, index)
+        totals = gather_columns(totals.reshape(1, -1), index).reshape(-1)
+    return M[:n_ann].cpu().numpy(), totals.cpu().numpy()
 
 
 # ---------------------------------------------------------------------------
