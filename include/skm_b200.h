@@ -171,6 +171,13 @@ SKM_API int skm_apply_dense(const int32_t *d_Q, int64_t nq, int64_t K,
                     void *workspace, size_t workspace_bytes,
                     skm_stream_t stream);
 
+/* Annotation-sharded apply (multi-GPU fan-in of apply.smk:312-335): merge per-shard top-2
+ * lists into the global top-2.  d_idx is int64 [n_shards, 2, nq] with GLOBAL annotation
+ * indices (-1 = no candidate), d_score float64 of the same shape.  Ties -> lowest index. */
+SKM_API int skm_top2_merge(const int64_t *d_idx, const double *d_score, int64_t n_shards,
+                   int64_t nq, int32_t *d_top1, int32_t *d_top2, double *d_score1,
+                   double *d_score2, skm_stream_t stream);
+
 /* row squared norms of an integer matrix (sklearn normalize, float64). */
 SKM_API int skm_row_norm2_i32(const int32_t *d_X, int64_t rows, int64_t cols,
                       double *d_out, skm_stream_t stream);

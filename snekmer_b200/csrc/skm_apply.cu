@@ -100,9 +100,38 @@ __global__ void __launch_bounds__(256) apply_top2_kernel(const int64_t *__restri
     }
 }
 
+// 2-way merge of per-shard top-2 lists (annotation-sharded apply): one thread per query
+__global__ void __launch_bounds__(256) top2_merge_kernel(const int64_t *__restrict__ idx, const double *__restrict__ score,
+                                                         int64_t n_shards, int64_t nq, int32_t *__restrict__ top1,
+                                                         int32_t *__restrict__ top2, double *__restrict__ sc1,
+                                                         double *__restrict__ sc2) {
+    for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < nq; q += int64_t(gridDim.x) * blockDim.x) {
+        Top2 t{0.0, 0.0, -1, -1};
+        for (int64_t w = 0; w < n_shards; ++w)
+            for (int j = 0; j < 2; ++j) {
+                const int64_t i = idx[(w * 2 + j) * nq + q];
+                if (i >= 0) top2_push(t, score[(w * 2 + j) * nq + q], int(i));
+            }
+        top1[q] = t.i1; sc1[q] = (t.i1 >= 0) ? t.s1 : 0.0;
+        top2[q] = t.i2; sc2[q] = (t.i2 >= 0) ? t.s2 : nan("");
+    }
+}
+
 }  // namespace skm
 
 extern "C" {
+
+int skm_top2_merge(const int64_t *d_idx, const double *d_score, int64_t n_shards, int64_t nq, int32_t *d_top1,
+                   int32_t *d_top2, double *d_score1, double *d_score2, skm_stream_t stream) {
+    using namespace skm;
+    if (n_shards < 0 || nq < 0) { set_error("skm_top2_merge: negative size"); return SKM_ERR_INVALID; }
+    if (nq == 0) return SKM_OK;
+    if (!d_top1 || !d_top2 || !d_score1 || !d_score2 || (n_shards > 0 && (!d_idx || !d_score))) { set_error("skm_top2_merge: NULL argument"); return SKM_ERR_INVALID; }
+    const int grid = (int)std::min<int64_t>((nq + 255) / 256, int64_t(sm_count()) * 8);
+    top2_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_idx, d_score, n_shards, nq, d_top1, d_top2, d_score1, d_score2);
+    SKM_LAUNCH_CHECK("top2_merge_kernel");
+    return SKM_OK;
+}
 
 size_t skm_apply_dense_workspace(int64_t nq, int64_t n_ann, int64_t K) {
     (void)K;

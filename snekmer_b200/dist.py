@@ -1,0 +1,136 @@
+"""dist: one process per GPU, ``torch.distributed`` (NCCL over NVLink; gloo in CPU tests).
+
+The reference fans out one Snakemake job per input FASTA (learn.smk:105-106,
+apply.smk:107-111) and fans in with one serial pandas merge (learn.smk:467-494).
+Here sequences are sharded by contiguous ranges balanced by residue count; the path
+has exactly three exchange steps, each a plain collective on integer / top-2 buffers:
+
+  basis   (kmerize.smk:89-104)   all_reduce(SUM) of per-code counts + all_reduce(MIN)
+                                 of first positions (global residue positions)
+  learn   (learn.smk:467-494)    all_reduce(SUM) of the dense count matrix / totals
+  apply   (apply.smk:312-335)    when the annotation matrix is row-(annotation-)sharded:
+                                 all_gather of per-shard (top1, top2, score1, score2) and a
+                                 2-way merge — top-2, not top-1: delta needs the runner-up
+
+encode / count / apply-with-replicated-M need no collective (weak scaling).
+Every function works on whatever device the tensors live on, so the collective
+plumbing is exercised on CPU with gloo (tests/test_dist_gloo.py); the compute around
+it is CUDA-only as everywhere else.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+INT64_MAX = np.iinfo(np.int64).max
+
+
+def init(backend: Optional[str] = None, device: Optional[torch.device] = None) -> Tuple[int, int]:
+    """Initialise the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun). Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return rank, world
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(offsets: np.ndarray, parts: int) -> List[Tuple[int, int]]:
+    """Cut N sequences into `parts` contiguous ranges with ~equal residue counts, only at
+    sequence boundaries.  Ranges may be empty; together they cover [0, N)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    if n <= 0:
+        return [(0, 0)] * parts
+    span = offsets[-1] - offsets[0]
+    targets = offsets[0] + (span * np.arange(1, parts, dtype=np.float64) / parts)
+    cuts = np.searchsorted(offsets[:-1], targets, side="left")
+    cuts = np.concatenate([[0], np.clip(cuts, 0, n), [n]]).astype(np.int64)
+    cuts = np.maximum.accumulate(cuts)
+    return [(int(cuts[i]), int(cuts[i + 1])) for i in range(parts)]
+
+
+def allreduce_basis_tables(count: torch.Tensor, first: torch.Tensor) -> None:
+    """Merge per-rank (count, first) tables of skm_basis_accumulate in place.
+
+    `first` holds uint64 bit patterns in int64 with all-ones (-1) = "never seen"; positions
+    are < 2^63, so mapping -1 to INT64_MAX makes a signed MIN correct."""
+    if world()[1] == 1:
+        return
+    dist.all_reduce(count, op=dist.ReduceOp.SUM)
+    f = torch.where(first < 0, torch.full_like(first, INT64_MAX), first)
+    dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    first.copy_(torch.where(f == INT64_MAX, torch.full_like(f, -1), f))
+
+
+def allreduce_sum_(*tensors: torch.Tensor) -> None:
+    """Learn-mode fan-in: integer sums of the per-rank count matrices / totals / sequence counts."""
+    if world()[1] == 1:
+        return
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def exclusive_prefix(value: int, device=None) -> Tuple[int, int]:
+    """(sum of `value` over lower ranks, sum over all ranks): global residue / sequence bases."""
+    rank, w = world()
+    if w == 1:
+        return 0, int(value)
+    t = torch.zeros(w, dtype=torch.int64, device=device)
+    t[rank] = int(value)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    v = t.cpu().numpy()
+    return int(v[:rank].sum()), int(v.sum())
+
+
+def allgather_top2(top1: torch.Tensor, top2: torch.Tensor, s1: torch.Tensor, s2: torch.Tensor,
+                   ann_base: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Annotation-sharded apply: every rank scored ALL queries against its slice of annotations.
+    Returns (idx [W, 2, Q] int64 global annotation indices or -1, score [W, 2, Q] float64)
+    stacked over ranks, ready for the 2-way merge (engine.merge_top2)."""
+    rank, w = world()
+    idx = torch.stack([top1.to(torch.int64), top2.to(torch.int64)])
+    idx = torch.where(idx >= 0, idx + int(ann_base), idx)
+    sc = torch.stack([s1.to(torch.float64), s2.to(torch.float64)])
+    if w == 1:
+        return idx.unsqueeze(0), sc.unsqueeze(0)
+    all_idx = [torch.empty_like(idx) for _ in range(w)]
+    all_sc = [torch.empty_like(sc) for _ in range(w)]
+    dist.all_gather(all_idx, idx.contiguous())
+    dist.all_gather(all_sc, sc.contiguous())
+    return torch.stack(all_idx), torch.stack(all_sc)
+
+
+def gather_rows(local: torch.Tensor, dst: int = 0) -> Optional[torch.Tensor]:
+    """Concatenate per-rank row blocks (different lengths) on `dst` in rank order (query-sharded outputs)."""
+    rank, w = world()
+    if w == 1:
+        return local
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(w)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(parts, pad)
+    if rank != dst:
+        return None
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+def barrier() -> None:
+    if world()[1] > 1:
+        dist.barrier()

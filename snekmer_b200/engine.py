@@ -508,3 +508,61 @@ def apply_dense(Q: torch.Tensor, M: torch.Tensor, qnorm2: Optional[torch.Tensor]
                                     _ptr(top1[q0:q1]), _ptr(top2[q0:q1]), _ptr(s1[q0:q1]), _ptr(s2[q0:q1]),
                                     None if scores is None else _ptr(scores[q0:q1]), _ptr(ws), ws_bytes, _stream()))
     return ApplyResult(top1, top2, s1, s2, scores)
+
+
+def merge_top2(idx: torch.Tensor, score: torch.Tensor) -> ApplyResult:
+    """Global top-2 from stacked per-shard top-2 lists (idx int64 [W, 2, Q] global annotation
+    indices or -1, score float64 [W, 2, Q]) — the fan-in of annotation-sharded apply."""
+    dev = _require_cuda(idx.device)
+    idx = idx.contiguous()
+    score = score.contiguous()
+    W, two, nq = idx.shape
+    assert two == 2 and tuple(score.shape) == (W, 2, nq) and idx.dtype == torch.int64 and score.dtype == torch.float64
+    top1 = torch.empty(nq, dtype=torch.int32, device=dev)
+    top2 = torch.empty(nq, dtype=torch.int32, device=dev)
+    s1 = torch.empty(nq, dtype=torch.float64, device=dev)
+    s2 = torch.empty(nq, dtype=torch.float64, device=dev)
+    check(lib().skm_top2_merge(_ptr(idx), _ptr(score), W, nq, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2), _stream()))
+    return ApplyResult(top1, top2, s1, s2, None)
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU compositions (one process per GPU; collectives in dist.py)
+# ---------------------------------------------------------------------------
+def build_basis_distributed(batch: SequenceBatch, alphabet, k: int, min_filter: int = 0, res_base: Optional[int] = None) -> Basis:
+    """The basis of the CONCATENATION of all ranks' shards (rank order), identical on every rank:
+    local tables with global first positions, all_reduce(SUM / MIN), local finalisation."""
+    from . import dist as D
+
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    if res_base is None:
+        res_base, _ = D.exclusive_prefix(batch.nres, batch.device)
+    count, first = basis_tables(S, batch.device)
+    basis_accumulate(batch, alphabet, k, count, first, res_base)
+    D.allreduce_basis_tables(count, first)
+    return basis_finalize(alphabet, k, count, first, min_filter)
+
+
+def learn_dense_distributed(batch: SequenceBatch, alphabet, k: int, basis: Optional[Basis], ann_id: torch.Tensor,
+                            n_ann: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """learn_dense on the local shard followed by the NCCL sum over ranks (the reference's
+    serial Merge step, learn.smk:467-494); every rank ends with the full matrix."""
+    from . import dist as D
+
+    M, totals = learn_dense(batch, alphabet, k, basis, ann_id, n_ann)
+    D.allreduce_sum_(M, totals)
+    return M, totals
+
+
+def apply_dense_annotation_sharded(Q: torch.Tensor, M_local: torch.Tensor, ann_base: int,
+                                   qnorm2: Optional[torch.Tensor] = None) -> ApplyResult:
+    """Every rank scores all queries against ITS rows of the annotation matrix; the per-shard
+    top-2 are all-gathered and merged (identical result on every rank)."""
+    from . import dist as D
+
+    r = apply_dense(Q, M_local, qnorm2=qnorm2)
+    idx, sc = D.allgather_top2(r.top1, r.top2, r.score1, r.score2, ann_base)
+    return merge_top2(idx, sc)

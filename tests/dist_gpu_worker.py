@@ -1,0 +1,63 @@
+"""Runs under torchrun (one rank per GPU, NCCL): the three exchange steps of the path on real
+shards, checked against the single-process oracle.  Launched by tests/test_dist_gpu.py."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import skm_oracle as O  # noqa: E402
+from snekmer_b200 import dist as D  # noqa: E402
+from snekmer_b200 import engine as E  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    rank, world = D.init("nccl", torch.device("cuda", local))
+    rng = np.random.default_rng(11)
+    aa = np.array(list("ACDEFGHIKLMNPQRSTVWYX"))
+    seqs = ["".join(rng.choice(aa, size=int(rng.integers(0, 400)))) for _ in range(3000)]
+    a, k, mf, n_ann = 2, 6, 1, 23
+    ann = rng.integers(-1, n_ann, size=len(seqs)).astype(np.int32)
+    res, off = O.pack(seqs)
+    lo, hi = D.shard_bounds(off, world)[rank]
+    batch = E.SequenceBatch.from_strings(seqs[lo:hi])
+    # basis of the concatenation, identical on all ranks
+    basis = E.build_basis_distributed(batch, a, k, mf)
+    lut, syms = O.build_lut(a)
+    si, pos, code, valid = O.window_codes(res, off, lut, len(syms), k)
+    want_basis, want_tot = O.basis_codes(si, pos, code, valid, mf)
+    assert np.array_equal(basis.codes_host(), want_basis), "distributed basis"
+    assert np.array_equal(basis.counts.cpu().numpy(), want_tot), "distributed basis counts"
+    # learn + NCCL sum
+    M, totals = E.learn_dense_distributed(batch, a, k, basis, torch.from_numpy(ann[lo:hi]), n_ann)
+    C = O.count_matrix(si, code, valid, len(seqs), want_basis).astype(np.int64)
+    want_M = np.zeros((n_ann + 1, len(want_basis)), dtype=np.int64)
+    np.add.at(want_M, np.where(ann < 0, n_ann, ann), C)
+    assert np.array_equal(M.cpu().numpy(), want_M), "distributed learn"
+    assert np.array_equal(totals.cpu().numpy(), C.sum(axis=0)), "distributed totals"
+    # apply, annotation-sharded: all queries everywhere, my slice of annotation rows
+    qbatch = E.SequenceBatch.from_strings(seqs[:500])
+    Q = E.count_dense(qbatch, a, k, basis)
+    rows = D.shard_bounds(np.arange(n_ann + 1), world)[rank]
+    r = E.apply_dense_annotation_sharded(Q, M[rows[0]:rows[1]].contiguous(), rows[0])
+    S = O.cosine_scores(C[:500], want_M[:n_ann])
+    i1, i2, s1, s2 = O.top2(S)
+    assert np.array_equal(r.top1.cpu().numpy(), i1) and np.array_equal(r.top2.cpu().numpy(), i2), "sharded top-2"
+    assert np.max(np.abs(r.score1.cpu().numpy() - s1)) < 1e-12 and np.max(np.abs(r.score2.cpu().numpy() - s2)) < 1e-12
+    # query-sharded apply with replicated M: concatenate on rank 0
+    rq = E.apply_dense(E.count_dense(batch, a, k, basis), M[:n_ann].contiguous())
+    allq = D.gather_rows(rq.top1.reshape(-1, 1), dst=0)
+    if rank == 0:
+        Sall = O.cosine_scores(C, want_M[:n_ann])
+        assert np.array_equal(allq.reshape(-1).cpu().numpy(), O.top2(Sall)[0]), "query-sharded apply"
+        print(f"dist_gpu_worker ok: world={world} K={basis.K}")
+    D.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
