@@ -157,6 +157,45 @@ SKM_API int skm_learn_dense(const uint8_t *d_residues, int64_t nres,
                     int64_t n_ann, int64_t *d_M, int64_t *d_totals,
                     skm_stream_t stream);
 
+/* (a12/a13 at large K) learn, sparse: every valid window of a sequence with d_ann_id[s] >= 0
+ * becomes the key ann * S + code (S = nsym^k < 2^32); keys are radix-sorted and run-length
+ * encoded (no atomics).  Output: a COO list sorted by key — d_keys_out / d_vals_out need
+ * capacity nres, the number of entries goes to *d_nnz (device int64).  Totals over all
+ * sequences (learn.smk:380) are the counts of skm_basis_accumulate.  < 2^31 residues per call. */
+SKM_API size_t skm_learn_sparse_workspace(int64_t nres);
+SKM_API int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets,
+                     int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                     const int32_t *d_ann_id, int64_t n_ann, uint64_t *d_keys_out,
+                     int64_t *d_vals_out, int64_t *d_nnz, void *workspace,
+                     size_t workspace_bytes, skm_stream_t stream);
+
+/* Merge.merge_dataframes (learn.smk:467-494) for sparse matrices / fan-in of per-GPU lists:
+ * entries with equal keys are summed; output sorted by key, capacity n, count in *d_n_out. */
+SKM_API size_t skm_coo_merge_workspace(int64_t n);
+SKM_API int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n,
+                  uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
+                  void *workspace, size_t workspace_bytes, skm_stream_t stream);
+
+/* Annotation-major COO (key = ann * S + code) -> k-mer-major CSC for the SpMM:
+ * d_colptr int64 [S+1], d_rows int32 [nnz] (annotation), d_w float [nnz] =
+ * M[a, c] / ||m_a|| (sklearn normalize, apply.smk:282), d_mnorm2 (nullable) = ||m_a||^2. */
+SKM_API size_t skm_csc_build_workspace(int64_t nnz, int64_t n_ann);
+SKM_API int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, int64_t S,
+                  int64_t n_ann, int64_t *d_colptr, int32_t *d_rows, float *d_w,
+                  double *d_mnorm2, void *workspace, size_t workspace_bytes,
+                  skm_stream_t stream);
+
+/* (a16/a17 at large K) apply as SpMM: queries are CSR rows over CODES (skm_count_csr with
+ * d_col_of_code = NULL, so that ||q|| runs over all valid k-mers, apply.smk:268-276);
+ * scores are accumulated in float32 (|rel. error| ~ 1e-7, tolerance of the path 1e-5).
+ * n_ann <= 51200 per call: shard the annotations and merge with skm_top2_merge.
+ * d_qnorm2 (nullable) receives ||q||^2. */
+SKM_API int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int32_t *d_vals,
+                     int64_t nq, const int64_t *d_colptr, const int32_t *d_rows,
+                     const float *d_w, int64_t n_ann, int32_t *d_top1, int32_t *d_top2,
+                     double *d_score1, double *d_score2, double *d_qnorm2,
+                     skm_stream_t stream);
+
 /* (a16/a17) apply: cosine_similarity + top-2, apply.smk:278-335 and
  * learn.smk:811-849.  Queries are int32 count rows [nq, K] over the same
  * columns as d_M (int64 [n_ann, K]); d_qnorm2 holds ||q||^2 over ALL valid

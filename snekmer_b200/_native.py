@@ -51,6 +51,13 @@ SIGNATURES = {
     "skm_learn_dense": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p]),
     "skm_apply_dense_workspace": (_sz, [_i64, _i64, _i64]),
     "skm_apply_dense": (_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "skm_learn_sparse_workspace": (_sz, [_i64]),
+    "skm_learn_sparse": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "skm_coo_merge_workspace": (_sz, [_i64]),
+    "skm_coo_merge": (_int, [_p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "skm_csc_build_workspace": (_sz, [_i64, _i64]),
+    "skm_csc_build": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "skm_apply_sparse": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "skm_top2_merge": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "skm_row_norm2_i32": (_int, [_p, _i64, _i64, _p, _p]),
     "skm_row_norm2_i64": (_int, [_p, _i64, _i64, _p, _p]),

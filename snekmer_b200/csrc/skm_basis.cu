@@ -22,27 +22,6 @@ namespace skm {
 
 constexpr int64_t SMALL_S = 16384;   // 8 B per code of shared memory -> 128 KB
 
-__device__ __forceinline__ int64_t lower_bound_off(const int64_t *__restrict__ off, int64_t n, int64_t target) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(off + mid) < target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// CTA i owns the sequences whose start lies in [R*i/G, R*(i+1)/G): contiguous and residue-balanced.
-__device__ __forceinline__ void cta_seq_range(const int64_t *__restrict__ off, int64_t nseq, int64_t *lo, int64_t *hi) {
-    const int64_t r0 = __ldg(off), r1 = __ldg(off + nseq);
-    const int64_t span = r1 - r0;
-    const int64_t G = gridDim.x, i = blockIdx.x;
-    const int64_t t0 = r0 + (int64_t)(((__int128)span * i) / G);
-    const int64_t t1 = r0 + (int64_t)(((__int128)span * (i + 1)) / G);
-    *lo = lower_bound_off(off, nseq, t0);
-    *hi = (i + 1 == G) ? nseq : lower_bound_off(off, nseq, t1);
-    if (i == 0) *lo = 0;
-}
-
 constexpr int BS_SEG = ts_seg_cap(52);              // residues per staged segment (52 per thread)
 constexpr int BS_SYM_BYTES = ts_sym_bytes(BS_SEG);
 

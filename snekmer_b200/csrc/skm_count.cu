@@ -136,36 +136,6 @@ __global__ void __launch_bounds__(TS_THREADS) count_dense_kernel(const uint8_t *
 // ---------------------------------------------------------------------------
 // sparse (CSR)
 // ---------------------------------------------------------------------------
-// keys[p] = column (or code) of the window starting at p, all-ones if invalid / not in the basis
-template <int NW>
-__global__ void __launch_bounds__(256) csr_keys_kernel(const uint8_t *__restrict__ res, int64_t nres,
-                                                       const int64_t *__restrict__ off, int64_t nseq,
-                                                       const uint8_t *__restrict__ lut, int nsym, int k,
-                                                       const int32_t *__restrict__ col_of_code, int64_t res0,
-                                                       uint32_t *__restrict__ keys) {
-    __shared__ uint8_t s_lut[256];
-    s_lut[threadIdx.x] = lut[threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t s = warp; s < nseq; s += nwarps) {
-        const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
-        const int64_t tail0 = (e - b >= k) ? e - k + 1 : b;
-        for (int64_t p = tail0 + lane; p < e; p += 32) keys[p - res0] = 0xFFFFFFFFu;
-        warp_scan_sequence<uint32_t, NW>(res, nres, b, e, s_lut, nsym, k, [&](int64_t g, uint32_t code, bool ok) {
-            if (g >= b && g <= e - k) {
-                uint32_t key = 0xFFFFFFFFu;
-                if (ok) {
-                    if (col_of_code) { const int32_t c = __ldg(col_of_code + code); if (c >= 0) key = uint32_t(c); }
-                    else key = code;
-                }
-                keys[g - res0] = key;
-            }
-        });
-    }
-}
-
 // one warp per sequence over its sorted keys: count (and optionally write) the runs
 __global__ void __launch_bounds__(256) csr_runs_kernel(const uint32_t *__restrict__ keys, const int64_t *__restrict__ off,
                                                        int64_t seq0, int64_t nseq, int64_t res0,
@@ -199,6 +169,10 @@ __global__ void __launch_bounds__(256) csr_runs_kernel(const uint32_t *__restric
 }
 
 }  // namespace skm
+
+extern "C" int skm_window_keys_u32(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                                   const uint8_t *d_lut, int nsym, int k, const int32_t *d_col_of_code, uint32_t *d_keys,
+                                   cudaStream_t st);   // skm_sparse.cu
 
 extern "C" {
 
@@ -307,11 +281,12 @@ int skm_count_csr(const uint8_t *d_residues, int64_t nres, const int64_t *d_offs
     uint32_t *keys_a = (uint32_t *)p, *keys_b = (uint32_t *)(p + seg);
     void *temp = p + 2 * seg;
     size_t temp_bytes = workspace_bytes - (size_t)((char *)temp - (char *)workspace);
+    if (!ts_supported(nsym, k)) { set_error("skm_count_csr: nsym=%d k=%d outside the kernel envelope", nsym, k); return SKM_ERR_UNSUPPORTED; }
     const int grid = sm_count() * 8;
-    const int nw = neighbour_words(k);
-    // keys are indexed by absolute position in d_residues (positions outside every sequence are never read)
-    SKM_DISPATCH_NW(nw, (csr_keys_kernel<NW><<<grid, 256, 0, st>>>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, 0, keys_a)));
-    SKM_LAUNCH_CHECK("csr_keys_kernel");
+    // keys are indexed by the absolute position of the window's last residue (positions outside every sequence
+    // are never read by the segmented sort)
+    rc = skm_window_keys_u32(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, keys_a, st);
+    if (rc) return rc;
     SKM_CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(temp, temp_bytes, keys_a, keys_b, (int)nres, (int)nseq, d_offsets,
                                                     d_offsets + 1, st));
     csr_runs_kernel<<<grid, 256, 0, st>>>(keys_b, d_offsets, 0, nseq, 0, d_rowptr, nullptr, nullptr);

@@ -177,6 +177,98 @@ __device__ __forceinline__ void ts_scan_chunk(uint32_t sym, int i0, int i1, int 
     for (; p < pend; ++p, ++q) ts_step<0>(p, q, uk, nsym, npow, run, code, emit, boundary);
 }
 
+__device__ __forceinline__ int64_t lower_bound_off(const int64_t *__restrict__ off, int64_t n, int64_t target) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// CTA i owns the sequences whose start lies in [R*i/G, R*(i+1)/G): contiguous and residue-balanced.
+__device__ __forceinline__ void cta_seq_range(const int64_t *__restrict__ off, int64_t nseq, int64_t *lo, int64_t *hi) {
+    const int64_t r0 = __ldg(off), r1 = __ldg(off + nseq);
+    const int64_t span = r1 - r0;
+    const int64_t G = gridDim.x, i = blockIdx.x;
+    const int64_t t0 = r0 + (int64_t)(((__int128)span * i) / G);
+    const int64_t t1 = r0 + (int64_t)(((__int128)span * (i + 1)) / G);
+    *lo = lower_bound_off(off, nseq, t0);
+    *hi = (i + 1 == G) ? nseq : lower_bound_off(off, nseq, t1);
+    if (i == 0) *lo = 0;
+}
+
+// ---- a CTA walks its share of the residue buffer, with the sequence index of every window -----------
+// Used by the kernels that need to know WHICH sequence a window belongs to while scanning a long
+// contiguous range (key generation for the sort-based sparse paths).  CTA i owns the sequences that
+// start in the i-th 1/gridDim of the buffer.  emit(rel_end, row, code, ok) is called for EVERY residue
+// position of the range: rel_end = position of the window's last residue minus `origin`,
+// row = index of the sequence that holds it, ok = the window is valid.
+// s_sym: ts_sym_bytes(seg_cap) bytes; s_lut: 256 bytes (ts_lut_init done, barrier passed);
+// s_ctl: 4 x int64 of shared scratch.
+template <typename CodeT, typename Emit>
+__device__ __forceinline__ void ts_range_scan_rows(const uint8_t *__restrict__ res, int64_t nres,
+                                                   const int64_t *__restrict__ off, int64_t nseq, const uint8_t *s_lut,
+                                                   uint8_t *s_sym, int seg_cap, int k, CodeT nsym, CodeT pow_k1,
+                                                   int64_t origin, int64_t *s_ctl, Emit &&emit) {
+    const int tid = threadIdx.x;
+    unsigned int *s_nstart = reinterpret_cast<unsigned int *>(s_ctl + 2);
+    if (tid == 0) { cta_seq_range(off, nseq, &s_ctl[0], &s_ctl[1]); *s_nstart = 0; }
+    __syncthreads();
+    const int64_t lo = s_ctl[0], hi = s_ctl[1];
+    if (lo >= hi) return;
+    uint32_t sym_addr = smem_addr(s_sym);
+    asm volatile("" : "+r"(sym_addr));
+    const int64_t r_lo = __ldg(off + lo), r_hi = __ldg(off + hi);
+    int64_t cur = lo;                 // first sequence that starts at or after `a`
+    bool first = true;
+    uint32_t tail = 0;
+    for (int64_t a = r_lo; a < r_hi;) {
+        const int64_t b = min(r_hi, (a + seg_cap) & ~int64_t(15));
+        if (!first) ts_tail_write(s_sym, tail, k);
+        const TsSeg g = ts_stage(res, nres, a, b, s_lut, s_sym);
+        __syncthreads();
+        if (first) ts_invalidate_front(s_sym, g);
+        unsigned int mine = 0;
+        for (int64_t s = cur + tid; s < hi; s += blockDim.x) {
+            const int64_t o = __ldg(off + s);
+            if (o >= b) break;
+            s_sym[g.lo + int(o - a)] |= uint8_t(SYM_FLAG);
+            ++mine;
+        }
+        if (mine) atomicAdd(s_nstart, mine);
+        __syncthreads();
+        const int64_t nstart = *s_nstart;
+        const int C = ts_chunk(g.hi - g.lo);
+        const int i0 = g.lo + tid * C, i1 = min(i0 + C, g.hi);
+        if (i0 < i1) {
+            // sequence holding position x0 = a + (i0 - g.lo): the last one of [cur-1, cur+nstart) that starts at or before x0
+            const int64_t x0 = a + (i0 - g.lo);
+            int64_t l = cur, h = cur + nstart;               // count of sequences in [cur, cur+nstart) with off <= x0 ...
+            while (l < h) {
+                const int64_t mid = (l + h) >> 1;
+                if (__ldg(off + mid) < x0) l = mid + 1; else h = mid;   // ... strictly before x0: a start AT x0 is flagged
+            }
+            int64_t row = l - 1;
+            const int64_t to_abs = (g.base - TS_PAD) - int64_t(sym_addr);    // absolute position = shared address + to_abs
+            const int64_t to_rel = to_abs - origin;
+            ts_scan_chunk<CodeT>(
+                sym_addr, i0, i1, k, nsym, pow_k1,
+                [&](uint32_t p, CodeT code, bool ok) { emit(int64_t(p) + to_rel, row, code, ok); },
+                [&](uint32_t p) {
+                    const int64_t pos = int64_t(p) + to_abs;
+                    do { ++row; } while (row + 1 < nseq && __ldg(off + row + 1) <= pos);   // skips empty sequences
+                });
+        }
+        tail = ts_tail_read(s_sym, g, k);
+        first = false;
+        cur += nstart;
+        a = b;
+        __syncthreads();
+        if (tid == 0) *s_nstart = 0;    // ordered before the next atomicAdd by the barrier after staging
+    }
+}
+
 inline bool ts_supported(int nsym, int k) { return nsym <= TS_MAX_NSYM && k <= TS_MAX_K; }
 
 // ---- bulk (TMA engine) shared -> global store -------------------------------------

@@ -527,6 +527,140 @@ def merge_top2(idx: torch.Tensor, score: torch.Tensor) -> ApplyResult:
 
 
 # ---------------------------------------------------------------------------
+# sparse paths (large bases): sort-based learn, CSC, SpMM apply
+# ---------------------------------------------------------------------------
+def _sub_batch(batch: SequenceBatch, lo: int, hi: int) -> SequenceBatch:
+    """Sequences [lo, hi) of a batch as a self-contained shard (same HBM buffer, rebased offsets)."""
+    oh = batch.offsets_host
+    base = int(oh[lo]) & ~15                      # keep the 16-byte alignment of the residue pointer
+    sub = SequenceBatch(batch.residues[base:], batch.offsets[lo:hi + 1] - base, oh[lo:hi + 1] - base)
+    sub.nres = int(oh[hi]) - base
+    return sub
+
+
+def _chunks_by_residues(offsets_host: np.ndarray, max_res: int):
+    n = len(offsets_host) - 1
+    out, lo = [], 0
+    while lo < n:
+        hi = int(np.searchsorted(offsets_host, offsets_host[lo] + max_res, side="right")) - 1
+        hi = min(max(hi, lo + 1), n)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def coo_merge(keys: torch.Tensor, vals: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sum entries with equal keys; result sorted by key (Merge.merge_dataframes for sparse matrices)."""
+    dev = _require_cuda(keys.device)
+    n = keys.numel()
+    keys, vals = keys.contiguous(), vals.contiguous()
+    ws_bytes = lib().skm_coo_merge_workspace(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    ov = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    dn = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_coo_merge(_ptr(keys), _ptr(vals), n, _ptr(ok), _ptr(ov), _ptr(dn), _ptr(ws), ws_bytes, _stream()))
+    m = int(dn.item())
+    return ok[:m].clone(), ov[:m].clone()
+
+
+def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int,
+                 max_chunk_res: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Annotation x k-mer count matrix as a COO list sorted by key = ann * S + code
+    (keys int64 holding the uint64 pattern, vals int64).  Sequences with ann_id < 0 do not
+    contribute (Totals come from the basis tables)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    assert ann_id.numel() == batch.n
+    parts_k, parts_v = [], []
+    for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
+        sub = _sub_batch(batch, lo, hi)
+        ws_bytes = lib().skm_learn_sparse_workspace(sub.nres)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ok = torch.empty(max(sub.nres, 1), dtype=torch.int64, device=dev)
+        ov = torch.empty(max(sub.nres, 1), dtype=torch.int64, device=dev)
+        dn = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(lib().skm_learn_sparse(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k),
+                                     _ptr(ann_id[lo:hi]), int(n_ann), _ptr(ok), _ptr(ov), _ptr(dn), _ptr(ws), ws_bytes,
+                                     _stream()))
+        m = int(dn.item())
+        parts_k.append(ok[:m].clone())
+        parts_v.append(ov[:m].clone())
+        del ws, ok, ov
+    if len(parts_k) == 1:
+        return parts_k[0], parts_v[0]
+    if not parts_k:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, z.clone()
+    return coo_merge(torch.cat(parts_k), torch.cat(parts_v))
+
+
+@dataclass
+class AnnotationCSC:
+    """k-mer-major view of an annotation slice [ann_lo, ann_lo + n_ann) with cosine weights."""
+    colptr: torch.Tensor    # int64 [S+1]
+    rows: torch.Tensor      # int32 [nnz] annotation index relative to ann_lo
+    w: torch.Tensor         # float32 [nnz] = M[a, c] / ||m_a||
+    mnorm2: torch.Tensor    # float64 [n_ann]
+    n_ann: int
+    ann_lo: int
+    S: int
+
+
+def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo: int = 0) -> AnnotationCSC:
+    """CSC of the annotation slice [ann_lo, ann_lo + n_ann) of a sorted COO matrix."""
+    dev = _require_cuda(keys.device)
+    if keys.numel():
+        # the slice is contiguous because the list is sorted by ann * S + code
+        bounds = torch.tensor([ann_lo * S, (ann_lo + n_ann) * S], dtype=torch.int64, device=dev)
+        i0, i1 = torch.searchsorted(keys, bounds).tolist()
+        keys = (keys[i0:i1] - ann_lo * S).contiguous()
+        vals = vals[i0:i1].contiguous()
+    nnz = keys.numel()
+    ws_bytes = lib().skm_csc_build_workspace(nnz, n_ann)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    colptr = torch.empty(S + 1, dtype=torch.int64, device=dev)
+    rows = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    w = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    mn2 = torch.zeros(max(n_ann, 1), dtype=torch.float64, device=dev)
+    check(lib().skm_csc_build(_ptr(keys), _ptr(vals), nnz, int(S), int(n_ann), _ptr(colptr), _ptr(rows), _ptr(w), _ptr(mn2),
+                              _ptr(ws), ws_bytes, _stream()))
+    return AnnotationCSC(colptr, rows[:nnz], w[:nnz], mn2[:n_ann], int(n_ann), int(ann_lo), int(S))
+
+
+SPARSE_MAX_ANN = 50 * 1024
+
+
+def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, csc: AnnotationCSC) -> ApplyResult:
+    """SpMM scoring of CSR queries (codes + counts, count_csr with basis=None) against one annotation slice."""
+    dev = _require_cuda(rowptr.device)
+    nq = rowptr.numel() - 1
+    top1 = torch.empty(nq, dtype=torch.int32, device=dev)
+    top2 = torch.empty(nq, dtype=torch.int32, device=dev)
+    s1 = torch.empty(nq, dtype=torch.float64, device=dev)
+    s2 = torch.empty(nq, dtype=torch.float64, device=dev)
+    check(lib().skm_apply_sparse(_ptr(rowptr), _ptr(cols), _ptr(vals), nq, _ptr(csc.colptr), _ptr(csc.rows), _ptr(csc.w),
+                                 csc.n_ann, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2), None, _stream()))
+    return ApplyResult(top1, top2, s1, s2, None)
+
+
+def apply_sparse_tiled(rowptr, cols, vals, keys, mvals, S: int, n_ann: int, tile: int = 8192) -> ApplyResult:
+    """All annotations of a sorted COO matrix, `tile` at a time, merged with the top-2 merge
+    (the same fan-in as the multi-GPU annotation sharding)."""
+    idxs, scs = [], []
+    for a0 in range(0, max(n_ann, 1), tile):
+        na = min(tile, n_ann - a0)
+        if na <= 0:
+            break
+        r = apply_sparse(rowptr, cols, vals, csc_build(keys, mvals, S, na, a0))
+        i = torch.stack([r.top1.to(torch.int64), r.top2.to(torch.int64)])
+        idxs.append(torch.where(i >= 0, i + a0, i))
+        scs.append(torch.stack([r.score1, r.score2]))
+    return merge_top2(torch.stack(idxs), torch.stack(scs))
+
+
+# ---------------------------------------------------------------------------
 # multi-GPU compositions (one process per GPU; collectives in dist.py)
 # ---------------------------------------------------------------------------
 def build_basis_distributed(batch: SequenceBatch, alphabet, k: int, min_filter: int = 0, res_base: Optional[int] = None) -> Basis:

@@ -247,3 +247,67 @@ def test_errors_are_loud():
         E.build_basis(batch, None, 8)           # 20^8 > table limit
     with pytest.raises(ValueError):
         E.encode_windows(batch, "nope", 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse paths
+# ---------------------------------------------------------------------------------------------
+def _dense_from_coo(keys, vals, S, n_ann):
+    k = keys.cpu().numpy().view(np.uint64)
+    M = np.zeros((n_ann, S), dtype=np.int64)
+    M[(k // np.uint64(S)).astype(np.int64), (k % np.uint64(S)).astype(np.int64)] = vals.cpu().numpy()
+    return M
+
+
+@pytest.mark.parametrize("a,k,chunk", [(2, 5, 1 << 28), (5, 3, 20000), (0, 10, 7000), (None, 3, 1 << 28)])
+def test_learn_sparse_matches_dense(a, k, chunk):
+    rng = np.random.default_rng(k * 7 + 1)
+    seqs = _rand_seqs(rng, 900, 0, 300)
+    seqs[4] = ""
+    batch = E.SequenceBatch.from_strings(seqs)
+    n_ann = 29
+    ann = rng.integers(-1, n_ann, size=len(seqs)).astype(np.int32)
+    keys, vals = E.learn_sparse(batch, a, k, torch.from_numpy(ann), n_ann, max_chunk_res=chunk)
+    kk = keys.cpu().numpy().view(np.uint64)
+    assert np.all(kk[1:] > kk[:-1])                      # sorted, distinct
+    _, (si, pos, code, valid), (res, offs, lut, syms) = _codes_oracle(seqs, a, k)
+    S = len(syms) ** k
+    full = O.count_matrix(si, code, valid, len(seqs), np.arange(S, dtype=np.uint64)).astype(np.int64)
+    want = np.zeros((n_ann, S), dtype=np.int64)
+    sel = ann >= 0
+    np.add.at(want, ann[sel], full[sel])
+    assert np.array_equal(_dense_from_coo(keys, vals, S, n_ann), want)
+    assert int(vals.min().item()) > 0
+    # merging a list with itself doubles every count
+    k2, v2 = E.coo_merge(torch.cat([keys, keys]), torch.cat([vals, vals]))
+    assert torch.equal(k2, keys) and torch.equal(v2, 2 * vals)
+
+
+@pytest.mark.parametrize("a,k,tile", [(2, 6, 8192), (5, 3, 7), (1, 4, 16)])
+def test_apply_sparse_matches_dense_oracle(a, k, tile):
+    rng = np.random.default_rng(k + 100)
+    train = _rand_seqs(rng, 1200, 20, 300)
+    n_ann = 37
+    ann = rng.integers(-1, n_ann, size=len(train)).astype(np.int32)
+    tb = E.SequenceBatch.from_strings(train)
+    keys, vals = E.learn_sparse(tb, a, k, torch.from_numpy(ann), n_ann)
+    queries = _rand_seqs(rng, 400, 0, 250) + train[:50] + ["", "AC"]
+    qb = E.SequenceBatch.from_strings(queries)
+    rowptr, cols, cvals = E.count_csr(qb, a, k, None)
+    _, (si, pos, code, valid), (res, offs, lut, syms) = _codes_oracle(queries, a, k)
+    S = len(syms) ** k
+    r = E.apply_sparse_tiled(rowptr, cols, cvals, keys, vals, S, n_ann, tile=tile)
+    Q = O.count_matrix(si, code, valid, len(queries), np.arange(S, dtype=np.uint64))
+    M = _dense_from_coo(keys, vals, S, n_ann)
+    Sc = O.cosine_scores(Q, M)
+    i1, i2, s1, s2 = O.top2(Sc)
+    g1, g2 = r.top1.cpu().numpy(), r.top2.cpu().numpy()
+    gs1, gs2 = r.score1.cpu().numpy(), r.score2.cpu().numpy()
+    assert np.allclose(gs1, s1, rtol=1e-5, atol=1e-7) and np.allclose(gs2, s2, rtol=1e-5, atol=1e-7)
+    rows = np.arange(len(queries))
+    # identical predictions wherever the reference's own ranking is not a float32-level tie
+    clear1 = (s1 - s2) > 1e-5 * np.maximum(s1, 1e-30)
+    assert np.array_equal(g1[clear1], i1[clear1])
+    assert np.allclose(Sc[rows, g1], s1, rtol=1e-5, atol=1e-7) and np.allclose(Sc[rows, g2], s2, rtol=1e-5, atol=1e-7)
+    zero = s1 == 0
+    assert np.array_equal(g1[zero], np.zeros(zero.sum(), dtype=g1.dtype))     # all-zero rows: prediction = column 0
