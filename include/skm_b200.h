@@ -210,6 +210,25 @@ SKM_API int skm_apply_dense(const int32_t *d_Q, int64_t nq, int64_t K,
                     void *workspace, size_t workspace_bytes,
                     skm_stream_t stream);
 
+/* (a16/a17) apply on the tensor cores (tcgen05.mma kind::i8, TMA-fed, TMEM accumulators) for
+ * dense bases with K <= 32768.  The integer GEMM is exact: query counts must fit 8 bits and
+ * the annotation matrix is split into n_planes <= 4 base-256 digit planes by
+ * skm_apply_tc_prepare (once per learned matrix; this call synchronises the stream to read
+ * back the largest entry).  d_planes needs skm_apply_tc_planes_bytes() bytes, 128-byte
+ * aligned.  skm_apply_tc writes *d_status = 1 (device int) when a query count exceeded 255:
+ * the outputs are then invalid and the caller must use skm_apply_dense.  Scores are
+ * dot * (1/||q||) * (1/||m||) in float64; outputs as skm_apply_dense. */
+SKM_API size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K);
+SKM_API int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes,
+                         size_t planes_bytes, int *n_planes_out, skm_stream_t stream);
+SKM_API size_t skm_apply_tc_workspace(int64_t nq, int64_t K);
+SKM_API int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_planes,
+                 int n_planes, int64_t n_ann, const double *d_qnorm2,
+                 const double *d_mnorm2, int32_t *d_top1, int32_t *d_top2,
+                 double *d_score1, double *d_score2, double *d_scores_full,
+                 int *d_status, void *workspace, size_t workspace_bytes,
+                 skm_stream_t stream);
+
 /* Annotation-sharded apply (multi-GPU fan-in of apply.smk:312-335): merge per-shard top-2
  * lists into the global top-2.  d_idx is int64 [n_shards, 2, nq] with GLOBAL annotation
  * indices (-1 = no candidate), d_score float64 of the same shape.  Ties -> lowest index. */

@@ -1,0 +1,396 @@
+// skm_apply_tc.cu — kernel (d), dense basis: cosine scoring on the 5th-gen tensor cores.
+//
+// Replaces sklearn.metrics.pairwise.cosine_similarity(M, Q).T + argsort top-2
+// (apply.smk:278-335, learn.smk:811-849) when the k-mer basis is dense (K <= 32768).
+//
+// Counts are integers, so the GEMM is done EXACTLY on the integer tensor-core path
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM) instead of TF32:
+//   Q (query counts, 0..255)  -> one uint8 plane            A operand, K-major
+//   M (annotation sums)       -> n_planes base-256 digits   B operands, K-major
+//   dot[q, a] = sum_j 256^j * (Q . M_j^T)[q, a]             exact while K * 255^2 < 2^31
+// and only the final scaling by 1 / (||q|| ||m||) is floating point (float64, like the
+// reference).  One CTA owns 128 queries and walks all annotation tiles of 128:
+//   warp 0      TMA producer: 128 x 128-byte boxes of Q and of every M plane (SWIZZLE_128B)
+//               into a multi-stage shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer: one elected lane issues 4 x n_planes tcgen05.mma (M=128, N=128,
+//               K=32) per stage, tcgen05.commit releases the stage / publishes the tile
+//   warps 2-5   epilogue: tcgen05.ld the int32 accumulators (lane = query row), recombine the
+//               digits in int64, scale, keep a running top-2 per query in registers
+// TMEM: n_planes x 128 columns per accumulator set, double-buffered when it fits 512 columns.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "skm_common.cuh"
+
+namespace skm {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 128, UK = 32;
+constexpr int MAX_PLANES = 4;
+constexpr int TILE_BYTES = BM * BK;            // 16 KB: one 128 x 128-byte operand tile
+constexpr int THREADS = 192;
+constexpr int64_t MAX_K = 32768;               // K * 255 * 255 < 2^31
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return uint64_t((addr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+// kind::i8: D = S32, A = B = unsigned 8-bit, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+
+struct Top2d {
+    double s1, s2;
+    int i1, i2;
+};
+
+template <int n_planes>
+__global__ void __launch_bounds__(THREADS, 1)
+apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_m,
+                int ann_pad, int64_t nq, int n_ann, int k_chunks, int stages, const double *__restrict__ qnorm2,
+                const double *__restrict__ mnorm2, int32_t *__restrict__ top1, int32_t *__restrict__ top2,
+                double *__restrict__ sc1, double *__restrict__ sc2, double *__restrict__ full) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * 8 + 4];      // full[8], empty[8], tmem_full[2], tmem_empty[2]
+    __shared__ uint32_t s_tmem;
+    __shared__ double s_inv_mn[2][BN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = uint32_t(1 + n_planes) * TILE_BYTES;
+    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[18]);
+    const int acc_stages = (n_planes * BN * 2 <= 512) ? 2 : 1;
+    const int acc_cols = n_planes * BN;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < uint32_t(acc_cols * acc_stages)) tmem_cols <<= 1;
+    const int n_tiles = (n_ann + BN - 1) / BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {        // TMEM allocation (whole warp), same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int64_t q0 = int64_t(blockIdx.x) * BM;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t dst = smem_base + stage * stage_bytes;
+                    const uint32_t bar = full0 + 8 * stage;
+                    mbar_arrive_expect_tx(bar, stage_bytes);
+                    tma_load_2d(dst, &map_q, bar, kc * BK, int(q0));
+#pragma unroll
+                    for (int j = 0; j < n_planes; ++j)
+                        tma_load_2d(dst + (1 + j) * TILE_BYTES, &map_m, bar, kc * BK, j * ann_pad + t * BN);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t % acc_stages;
+                const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
+                mbar_wait(tempty0 + 8 * as, aphase ^ 1);       // epilogue has drained this accumulator set
+                tc_fence_after();
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * stage_bytes;
+#pragma unroll
+                    for (int j = 0; j < n_planes; ++j) {
+                        const uint32_t b_addr = a_addr + (1 + j) * TILE_BYTES;
+                        const uint32_t d = tmem_base + uint32_t(as * acc_cols + j * BN);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UK; ++kk)
+                            umma_i8(d, smem_desc(a_addr + kk * UK), smem_desc(b_addr + kk * UK), IDESC, (kc | kk) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * stage);            // stage free once these MMAs have read it
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * as);                   // accumulators of tile t complete
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int64_t q = q0 + row;
+        const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
+        const double qn2 = (q < nq) ? qnorm2[q] : 0.0;
+        const double inv_qn = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
+        Top2d best{0.0, 0.0, -1, -1};
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t % acc_stages;
+            const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
+            {   // 1 / ||m_a|| of this tile (double-buffered by tile parity)
+                const int a = t * BN + et;
+                const double m2 = (a < n_ann) ? mnorm2[a] : 0.0;
+                s_inv_mn[t & 1][et] = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * acc_cols);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[n_planes][16];
+#pragma unroll
+                for (int j = 0; j < n_planes; ++j) tmem_ld16(lane_addr + uint32_t(j * BN + c0), r[j]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int a = t * BN + c0 + i;
+                    int64_t dot = 0;
+#pragma unroll
+                    for (int j = n_planes - 1; j >= 0; --j) dot = (dot << 8) + int64_t(int32_t(r[j][i]));
+                    const double s = double(dot) * (inv_qn * s_inv_mn[t & 1][c0 + i]);
+                    if (a < n_ann) {
+                        if (full && q < nq) full[q * int64_t(n_ann) + a] = s;
+                        // ascending scan with strict '>' keeps the lowest index among ties
+                        if (best.i1 < 0 || s > best.s1) { best.s2 = best.s1; best.i2 = best.i1; best.s1 = s; best.i1 = a; }
+                        else if (best.i2 < 0 || s > best.s2) { best.s2 = s; best.i2 = a; }
+                    }
+                }
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);        // 4 arrivals (one per epilogue warp) free the set
+        }
+        if (q < nq) {
+            top1[q] = best.i1; sc1[q] = best.i1 >= 0 ? best.s1 : 0.0;
+            top2[q] = best.i2; sc2[q] = best.i2 >= 0 ? best.s2 : nan("");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---- operand preparation ------------------------------------------------------------------------
+// Q int32 [nq, K] -> uint8 [nq, Kp] (zero padded); *flag |= 1 if a count does not fit 8 bits
+__global__ void __launch_bounds__(256) split_q_kernel(const int32_t *__restrict__ Q, int64_t nq, int64_t K, int64_t Kp,
+                                                      uint8_t *__restrict__ out, int *__restrict__ flag) {
+    const int64_t total = nq * (Kp >> 2);
+    bool bad = false;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / (Kp >> 2), c = (i - r * (Kp >> 2)) << 2;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int32_t v = (c + j < K) ? __ldg(Q + r * K + c + j) : 0;
+            bad |= (v < 0 || v > 255);
+            w |= uint32_t(v & 0xFF) << (8 * j);
+        }
+        reinterpret_cast<uint32_t *>(out + r * Kp)[c >> 2] = w;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+// M int64 [A, K] -> planes uint8 [n_planes, Apad, Kp]: digit j of M in base 256 (rows/cols beyond A, K are zero)
+__global__ void __launch_bounds__(256) split_m_kernel(const int64_t *__restrict__ M, int64_t A, int64_t K, int64_t Apad,
+                                                      int64_t Kp, int n_planes, uint8_t *__restrict__ out) {
+    const int64_t total = Apad * Kp;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t a = i / Kp, c = i - a * Kp;
+        const uint64_t v = (a < A && c < K) ? uint64_t(__ldg(M + a * K + c)) : 0ull;
+        for (int j = 0; j < n_planes; ++j) out[(int64_t(j) * Apad + a) * Kp + c] = uint8_t(v >> (8 * j));
+    }
+}
+__global__ void __launch_bounds__(256) max_i64_kernel(const int64_t *__restrict__ X, int64_t n, unsigned long long *__restrict__ out) {
+    unsigned long long m = 0;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t v = X[i];
+        const unsigned long long u = v < 0 ? ~0ull : (unsigned long long)v;     // negative counts are not representable
+        m = u > m ? u : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, m, o); m = x > m ? x : m; }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+static PFN_cuTensorMapEncodeTiled encode_fn() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+// uint8 matrix [rows, Kp] row-major, boxes of 128 rows x 128 bytes, 128-byte swizzle, zero fill outside
+static int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t Kp) {
+    PFN_cuTensorMapEncodeTiled fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SKM_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp};
+    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return SKM_ERR_CUDA; }
+    return SKM_OK;
+}
+
+static int64_t pad128(int64_t x) { return (x + 127) & ~int64_t(127); }
+
+}  // namespace tc
+}  // namespace skm
+
+extern "C" {
+
+size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K) {
+    using namespace skm::tc;
+    if (n_ann <= 0 || K <= 0) return 256;
+    return size_t(MAX_PLANES) * size_t(pad128(n_ann)) * size_t(pad128(K)) + 256;
+}
+
+int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes, size_t planes_bytes,
+                         int *n_planes_out, skm_stream_t stream) {
+    using namespace skm;
+    using namespace skm::tc;
+    if (!n_planes_out) { set_error("skm_apply_tc_prepare: n_planes_out is NULL"); return SKM_ERR_INVALID; }
+    *n_planes_out = 0;
+    if (n_ann <= 0 || K <= 0) { set_error("skm_apply_tc_prepare: empty matrix"); return SKM_ERR_INVALID; }
+    if (K > MAX_K) { set_error("skm_apply_tc_prepare: K=%lld > %lld (int32 accumulators would overflow); use skm_apply_dense", (long long)K, (long long)MAX_K); return SKM_ERR_UNSUPPORTED; }
+    if (!d_M || !d_planes || planes_bytes < skm_apply_tc_planes_bytes(n_ann, K)) { set_error("skm_apply_tc_prepare: bad buffers"); return SKM_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(d_planes) & 127u) != 0) { set_error("skm_apply_tc_prepare: d_planes must be 128-byte aligned"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // the largest entry decides the number of base-256 digit planes (uses the head of d_planes as scratch)
+    unsigned long long *d_max = reinterpret_cast<unsigned long long *>(d_planes);
+    SKM_CUDA_TRY(cudaMemsetAsync(d_max, 0, 8, st));
+    const int64_t n = n_ann * K;
+    max_i64_kernel<<<(int)std::min<int64_t>((n + 255) / 256, int64_t(sm_count()) * 8), 256, 0, st>>>(d_M, n, d_max);
+    SKM_LAUNCH_CHECK("max_i64_kernel");
+    unsigned long long h_max = 0;
+    SKM_CUDA_TRY(cudaMemcpyAsync(&h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    SKM_CUDA_TRY(cudaStreamSynchronize(st));
+    int planes = 1;
+    while (planes < 8 && (h_max >> (8 * planes)) != 0) ++planes;
+    if (planes > MAX_PLANES) { set_error("skm_apply_tc_prepare: entries up to %llu need %d digit planes (> %d); use skm_apply_dense", h_max, planes, MAX_PLANES); return SKM_ERR_UNSUPPORTED; }
+    const int64_t Apad = pad128(n_ann), Kp = pad128(K);
+    split_m_kernel<<<(int)std::min<int64_t>((Apad * Kp + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_M, n_ann, K, Apad, Kp, planes, d_planes);
+    SKM_LAUNCH_CHECK("split_m_kernel");
+    *n_planes_out = planes;
+    return SKM_OK;
+}
+
+size_t skm_apply_tc_workspace(int64_t nq, int64_t K) {
+    using namespace skm::tc;
+    if (nq <= 0 || K <= 0) return 512;
+    return size_t(nq) * size_t(pad128(K)) + 512;
+}
+
+int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_planes, int n_planes, int64_t n_ann,
+                 const double *d_qnorm2, const double *d_mnorm2, int32_t *d_top1, int32_t *d_top2, double *d_score1,
+                 double *d_score2, double *d_scores_full, int *d_status, void *workspace, size_t workspace_bytes,
+                 skm_stream_t stream) {
+    using namespace skm;
+    using namespace skm::tc;
+    if (nq < 0 || K <= 0 || K > MAX_K || n_ann <= 0 || n_ann > 0x7FFFFF00ll || n_planes < 1 || n_planes > MAX_PLANES) { set_error("skm_apply_tc: bad sizes (K=%lld n_ann=%lld planes=%d)", (long long)K, (long long)n_ann, n_planes); return SKM_ERR_INVALID; }
+    if (nq == 0) return SKM_OK;
+    if (nq > 0x7FFFFF00ll) { set_error("skm_apply_tc: more than 2^31 queries per call"); return SKM_ERR_UNSUPPORTED; }
+    if (!d_Q || !d_planes || !d_qnorm2 || !d_mnorm2 || !d_top1 || !d_top2 || !d_score1 || !d_score2 || !d_status) { set_error("skm_apply_tc: NULL argument"); return SKM_ERR_INVALID; }
+    const size_t need = skm_apply_tc_workspace(nq, K);
+    if (!workspace || workspace_bytes < need) { set_error("skm_apply_tc: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Kp = pad128(K), Apad = pad128(n_ann);
+    uint8_t *q8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    SKM_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    split_q_kernel<<<(int)std::min<int64_t>((nq * (Kp >> 2) + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_Q, nq, K, Kp, q8, d_status);
+    SKM_LAUNCH_CHECK("split_q_kernel");
+    alignas(64) CUtensorMap map_q, map_m;
+    int rc = make_map(&map_q, q8, nq, Kp);
+    if (rc) return rc;
+    rc = make_map(&map_m, d_planes, int64_t(n_planes) * Apad, Kp);
+    if (rc) return rc;
+    const uint32_t stage_bytes = uint32_t(1 + n_planes) * TILE_BYTES;
+    int stages = int((200 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("skm_apply_tc: pipeline does not fit shared memory"); return SKM_ERR_UNSUPPORTED; }
+    const size_t smem = size_t(stages) * stage_bytes + 1024;
+    const unsigned grid = (unsigned)((nq + BM - 1) / BM);
+#define SKM_LAUNCH_TC(NP)                                                                                                    \
+    {                                                                                                                        \
+        auto kern = apply_tc_kernel<NP>;                                                                                     \
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        kern<<<grid, THREADS, smem, st>>>(map_q, map_m, (int)Apad, nq, (int)n_ann, (int)(Kp / BK), stages, d_qnorm2, d_mnorm2, \
+                                          d_top1, d_top2, d_score1, d_score2, d_scores_full);                                \
+    }
+    switch (n_planes) {
+        case 1: SKM_LAUNCH_TC(1) break;
+        case 2: SKM_LAUNCH_TC(2) break;
+        case 3: SKM_LAUNCH_TC(3) break;
+        default: SKM_LAUNCH_TC(4) break;
+    }
+#undef SKM_LAUNCH_TC
+    SKM_LAUNCH_CHECK("apply_tc_kernel");
+    return SKM_OK;
+}
+
+}  // extern "C"

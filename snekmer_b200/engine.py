@@ -479,11 +479,72 @@ class ApplyResult:
     scores: Optional[torch.Tensor] = None   # float64 [Q, A] when requested
 
 
+TC_MAX_K = 32768
+
+
+@dataclass
+class PreparedAnnotations:
+    """An annotation matrix split into base-256 digit planes for the tensor-core scoring kernel."""
+    planes: torch.Tensor        # uint8 buffer [n_planes, pad128(A), pad128(K)]
+    n_planes: int
+    n_ann: int
+    K: int
+    mnorm2: torch.Tensor        # float64 [A]
+
+
+def prepare_annotations(M: torch.Tensor, mnorm2: Optional[torch.Tensor] = None) -> Optional[PreparedAnnotations]:
+    """Digit planes of M for apply_tc, or None when M is outside the tensor-core envelope
+    (K > 32768, entries >= 2^32 or negative).  Do this once per learned matrix."""
+    M = M.contiguous()
+    A, K = M.shape
+    if A == 0 or K == 0 or K > TC_MAX_K:
+        return None
+    dev = _require_cuda(M.device)
+    nbytes = lib().skm_apply_tc_planes_bytes(A, K)
+    planes = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    n_planes = _native.C.c_int(0)
+    rc = lib().skm_apply_tc_prepare(_ptr(M), A, K, _ptr(planes), nbytes, _native.C.byref(n_planes), _stream())
+    if rc == -3:            # SKM_ERR_UNSUPPORTED: too many digit planes
+        return None
+    check(rc)
+    return PreparedAnnotations(planes, int(n_planes.value), A, K, row_norm2(M) if mnorm2 is None else mnorm2)
+
+
+def apply_tc(Q: torch.Tensor, prep: PreparedAnnotations, qnorm2: Optional[torch.Tensor] = None,
+             full: bool = False) -> Optional[ApplyResult]:
+    """Tensor-core scoring (tcgen05 int8 GEMM, exact integer dots).  Returns None when a query
+    count exceeds 255 (the caller then uses the exact CUDA-core path)."""
+    dev = _require_cuda(Q.device)
+    Q = Q.contiguous()
+    nq, K = Q.shape
+    assert K == prep.K and Q.dtype == torch.int32
+    if qnorm2 is None:
+        qnorm2 = row_norm2(Q)
+    A = prep.n_ann
+    top1 = torch.empty(nq, dtype=torch.int32, device=dev)
+    top2 = torch.empty(nq, dtype=torch.int32, device=dev)
+    s1 = torch.empty(nq, dtype=torch.float64, device=dev)
+    s2 = torch.empty(nq, dtype=torch.float64, device=dev)
+    scores = torch.empty((nq, A), dtype=torch.float64, device=dev) if full else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib().skm_apply_tc_workspace(nq, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().skm_apply_tc(_ptr(Q), nq, K, _ptr(prep.planes), prep.n_planes, A, _ptr(qnorm2), _ptr(prep.mnorm2), _ptr(top1),
+                             _ptr(top2), _ptr(s1), _ptr(s2), _ptr(scores), _ptr(status), _ptr(ws), ws_bytes, _stream()))
+    if int(status.item()) != 0:
+        return None
+    return ApplyResult(top1, top2, s1, s2, scores)
+
+
 def apply_dense(Q: torch.Tensor, M: torch.Tensor, qnorm2: Optional[torch.Tensor] = None,
-                mnorm2: Optional[torch.Tensor] = None, full: bool = False, chunk: int = 1 << 16) -> ApplyResult:
+                mnorm2: Optional[torch.Tensor] = None, full: bool = False, chunk: int = 1 << 16,
+                tensor_cores: Optional[bool] = None, prepared: Optional[PreparedAnnotations] = None) -> ApplyResult:
     """Cosine of every query count row against every annotation row + top-2
     (apply.smk:278-335).  Q int32 [nq, K], M int64 [A, K]; qnorm2 defaults to the
-    norm over Q's own columns."""
+    norm over Q's own columns.  tensor_cores: None = use the tcgen05 path when the
+    operands fit its exactness envelope and the problem is large enough to pay for the
+    operand split; True / False force the choice (True still falls back when the envelope
+    is violated)."""
     dev = Q.device
     Q = Q.contiguous()
     M = M.contiguous()
@@ -493,7 +554,14 @@ def apply_dense(Q: torch.Tensor, M: torch.Tensor, qnorm2: Optional[torch.Tensor]
     if qnorm2 is None:
         qnorm2 = row_norm2(Q)
     if mnorm2 is None:
-        mnorm2 = row_norm2(M)
+        mnorm2 = row_norm2(M) if prepared is None else prepared.mnorm2
+    want_tc = tensor_cores if tensor_cores is not None else (nq * A * K >= (1 << 24))
+    if want_tc and nq > 0 and A > 0 and 0 < K <= TC_MAX_K:
+        prep = prepared if prepared is not None else prepare_annotations(M, mnorm2)
+        if prep is not None:
+            r = apply_tc(Q, prep, qnorm2, full)
+            if r is not None:
+                return r
     top1 = torch.empty(nq, dtype=torch.int32, device=dev)
     top2 = torch.empty(nq, dtype=torch.int32, device=dev)
     s1 = torch.empty(nq, dtype=torch.float64, device=dev)

@@ -311,3 +311,50 @@ def test_apply_sparse_matches_dense_oracle(a, k, tile):
     assert np.allclose(Sc[rows, g1], s1, rtol=1e-5, atol=1e-7) and np.allclose(Sc[rows, g2], s2, rtol=1e-5, atol=1e-7)
     zero = s1 == 0
     assert np.array_equal(g1[zero], np.zeros(zero.sum(), dtype=g1.dtype))     # all-zero rows: prediction = column 0
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core scoring (tcgen05 int8 GEMM): bit-for-bit the same top-2 as the exact CUDA-core path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,A,K,mmax", [(300, 40, 1000, 200), (1000, 513, 257, 70000), (129, 128, 128, 2 ** 24 + 5),
+                                         (64, 3, 3000, 2 ** 31 - 1), (257, 700, 6561, 5000)])
+def test_apply_tensor_cores_match_exact_path(nq, A, K, mmax):
+    rng = np.random.default_rng(nq + A + K)
+    Q = rng.integers(0, 6, size=(nq, K)).astype(np.int32) * (rng.random((nq, K)) < 0.3)
+    Q[0] = 0
+    Q[1, :5] = 255
+    M = (rng.integers(0, mmax + 1, size=(A, K), dtype=np.int64) * (rng.random((A, K)) < 0.5)).astype(np.int64)
+    M[A // 2] = M[0]                       # an exact tie between two annotations
+    if A > 2:
+        M[A - 1] = 0                       # a zero-norm annotation
+    M[0, 0] = mmax
+    dQ, dM = torch.from_numpy(Q.astype(np.int32)).cuda(), torch.from_numpy(M).cuda()
+    exact = E.apply_dense(dQ, dM, full=True, tensor_cores=False)
+    prep = E.prepare_annotations(dM)
+    assert prep is not None and prep.n_planes == max(1, (int(mmax).bit_length() + 7) // 8)
+    tc = E.apply_tc(dQ, prep, full=True)
+    assert tc is not None
+    torch.cuda.synchronize()
+    # integer dots are exact on both paths; the scaling differs by <= 2 ulp
+    assert torch.allclose(tc.scores, exact.scores, rtol=1e-14, atol=0)
+    S = O.cosine_scores(Q, M)
+    assert np.max(np.abs(tc.scores.cpu().numpy() - S)) < 1e-12
+    i1, i2, s1, s2 = O.top2(tc.scores.cpu().numpy())
+    assert np.array_equal(tc.top1.cpu().numpy(), i1) and np.array_equal(tc.top2.cpu().numpy(), i2)
+    assert np.array_equal(tc.score1.cpu().numpy(), s1) and np.array_equal(tc.score2.cpu().numpy(), s2)
+    assert tc.top1[0].item() == 0 and tc.score1[0].item() == 0.0
+    # via the dispatcher, and without the full matrix
+    r = E.apply_dense(dQ, dM, tensor_cores=True, prepared=prep)
+    assert torch.equal(r.top1, tc.top1) and torch.equal(r.score2, tc.score2)
+
+
+def test_apply_tensor_cores_envelope_fallbacks():
+    Q = torch.zeros((10, 64), dtype=torch.int32).cuda()
+    Q[3, 7] = 300                                        # does not fit 8 bits -> exact path
+    M = torch.ones((5, 64), dtype=torch.int64).cuda()
+    prep = E.prepare_annotations(M)
+    assert E.apply_tc(Q, prep) is None
+    r = E.apply_dense(Q, M, tensor_cores=True)
+    assert r.top1[3].item() == 0 and abs(r.score1[3].item() - 300 / (300 * 8.0)) < 1e-15
+    M[2, 2] = 2 ** 40                                    # needs 6 digit planes
+    assert E.prepare_annotations(M) is None
