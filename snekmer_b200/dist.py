@@ -131,6 +131,28 @@ def gather_rows(local: torch.Tensor, dst: int = 0) -> Optional[torch.Tensor]:
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
 
 
+def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sparse learn fan-in (learn.smk:467-494 for COO matrices): rank r receives from every rank the
+    entries whose key lies in [key_bounds[r], key_bounds[r+1]).  `keys` must be sorted (int64 holding
+    non-negative keys), so each destination is one contiguous run.  The received runs still have to be
+    merged (engine.coo_merge).  key_bounds has world+1 entries."""
+    rank, w = world()
+    if w == 1:
+        return keys, vals
+    b = torch.tensor(list(key_bounds), dtype=torch.int64, device=keys.device)
+    cut = torch.searchsorted(keys, b)
+    send = (cut[1:] - cut[:-1]).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    lo, hi = int(cut[0].item()), int(cut[-1].item())
+    out_k = torch.empty(sum(recv_l), dtype=keys.dtype, device=keys.device)
+    out_v = torch.empty(sum(recv_l), dtype=vals.dtype, device=vals.device)
+    dist.all_to_all_single(out_k, keys[lo:hi].contiguous(), recv_l, send_l)
+    dist.all_to_all_single(out_v, vals[lo:hi].contiguous(), recv_l, send_l)
+    return out_k, out_v
+
+
 def barrier() -> None:
     if world()[1] > 1:
         dist.barrier()

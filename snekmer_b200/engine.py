@@ -768,3 +768,16 @@ def apply_dense_annotation_sharded(Q: torch.Tensor, M_local: torch.Tensor, ann_b
     r = apply_dense(Q, M_local, qnorm2=qnorm2)
     idx, sc = D.allgather_top2(r.top1, r.top2, r.score1, r.score2, ann_base)
     return merge_top2(idx, sc)
+
+
+def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Multi-GPU fan-in of sparse learn: annotations are split into equal ranges, rank r ends up with
+    the merged rows [n_ann*r/W, n_ann*(r+1)/W) of the matrix — the annotation sharding apply uses."""
+    from . import dist as D
+
+    rank, w = D.world()
+    if w == 1:
+        return keys, vals
+    bounds = [(n_ann * r // w) * S for r in range(w)] + [n_ann * S]
+    k2, v2 = D.alltoall_coo_by_key_range(keys, vals, bounds)
+    return coo_merge(k2, v2)

@@ -98,6 +98,17 @@ def _worker(rank, world, port, tmp):
             ok = cand_i[q] >= 0
             order = sorted(zip(-cand_s[q][ok], cand_i[q][ok]))
             assert order[0][1] == w1[q] and order[1][1] == w2[q]
+        # ---- sparse learn fan-in: all_to_all of sorted COO runs by annotation range ------------------
+        Sp = 1000
+        sel = ann[lo:hi] >= 0
+        kk = (ann[lo:hi][sel].astype(np.int64)[:, None] * Sp + np.arange(3)[None, :] * 7 + (np.arange(sel.sum()) % 5)[:, None]).reshape(-1)
+        uk, cnt = np.unique(kk, return_counts=True)
+        bounds = [(n_ann * r // world) * Sp for r in range(world)] + [n_ann * Sp]
+        rk, rv = D.alltoall_coo_by_key_range(torch.from_numpy(uk), torch.from_numpy(cnt.astype(np.int64)), bounds)
+        assert rk.numel() == rv.numel() and (rk >= bounds[rank]).all() and (rk < bounds[rank + 1]).all()
+        tot = torch.tensor([int(rv.sum()), int(cnt.sum())])
+        dist.all_reduce(tot)
+        assert tot[0].item() == tot[1].item()                 # nothing lost, nothing duplicated
         # ---- query-sharded outputs concatenated in rank order ---------------------------------
         mine = torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1)
         allrows = D.gather_rows(mine, dst=0)
