@@ -20,6 +20,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "skm_common.cuh"
 
 namespace skm {
@@ -91,30 +94,43 @@ struct Top2d {
     double s1, s2;
     int i1, i2;
 };
+// higher score first; equal scores -> lower ORIGINAL annotation index (np.argsort(-S) on exact ties)
+__device__ __forceinline__ void top2d_push(Top2d &t, double s, int i) {
+    if (t.i1 < 0 || s > t.s1 || (s == t.s1 && i < t.i1)) { t.s2 = t.s1; t.i2 = t.i1; t.s1 = s; t.i1 = i; }
+    else if (t.i2 < 0 || s > t.s2 || (s == t.s2 && i < t.i2)) { t.s2 = s; t.i2 = i; }
+}
 
-template <int n_planes>
+// Annotation rows are stored sorted by magnitude class (perm[sorted] = original index), so that a tile of 128
+// rows only carries the digit planes its largest entry needs (tile_planes[t] <= MAXP): small annotations — the
+// bulk of a Zipf-like family size distribution — cost one or two int8 GEMM passes instead of MAXP.
+// RESIDENT: the whole 128-query operand (k_chunks x 16 KB) stays in shared memory for the CTA's lifetime and
+// only annotation tiles stream through the ring (K <= 1024); otherwise query chunks travel through the ring too.
+template <int MAXP, bool RESIDENT>
 __global__ void __launch_bounds__(THREADS, 1)
-apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_m,
-                int ann_pad, int64_t nq, int n_ann, int k_chunks, int stages, const double *__restrict__ qnorm2,
+apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_m, int ann_pad,
+                int64_t nq, int n_ann, int k_chunks, int slots, const int32_t *__restrict__ perm,
+                const int32_t *__restrict__ tile_planes, const double *__restrict__ qnorm2,
                 const double *__restrict__ mnorm2, int32_t *__restrict__ top1, int32_t *__restrict__ top2,
                 double *__restrict__ sc1, double *__restrict__ sc2, double *__restrict__ full) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * 8 + 4];      // full[8], empty[8], tmem_full[2], tmem_empty[2]
+    __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 1];   // full[8], empty[8], tmem_full[2], tmem_empty[2], q_full
     __shared__ uint32_t s_tmem;
     __shared__ double s_inv_mn[2][BN];
+    __shared__ int32_t s_orig[2][BN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = uint32_t(1 + n_planes) * TILE_BYTES;
-    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[18]);
-    const int acc_stages = (n_planes * BN * 2 <= 512) ? 2 : 1;
-    const int acc_cols = n_planes * BN;
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < uint32_t(acc_cols * acc_stages)) tmem_cols <<= 1;
+    const uint32_t q_bytes = RESIDENT ? uint32_t(k_chunks) * TILE_BYTES : 0u;
+    const uint32_t ring_base = smem_base + q_bytes;
+    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[18]), qfull = s2u(&bars[20]);
+    constexpr int acc_stages = (MAXP * BN * 2 <= 512) ? 2 : 1;
+    constexpr int acc_cols = MAXP * BN;
+    constexpr uint32_t tmem_cols = (acc_cols * acc_stages <= 128) ? 128 : (acc_cols * acc_stages <= 256 ? 256 : 512);
     const int n_tiles = (n_ann + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < slots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        mbar_init(qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // TMEM allocation (whole warp), same warp frees it
@@ -130,46 +146,59 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
+            if (RESIDENT) {
+                mbar_arrive_expect_tx(qfull, q_bytes);
+                for (int kc = 0; kc < k_chunks; ++kc) tma_load_2d(smem_base + kc * TILE_BYTES, &map_q, qfull, kc * BK, int(q0));
+            }
+            int slot = 0;
             uint32_t phase = 0;
+            auto push = [&](const CUtensorMap *map, int c0, int c1) {
+                mbar_wait(empty0 + 8 * slot, phase ^ 1);
+                mbar_arrive_expect_tx(full0 + 8 * slot, TILE_BYTES);
+                tma_load_2d(ring_base + slot * TILE_BYTES, map, full0 + 8 * slot, c0, c1);
+                if (++slot == slots) { slot = 0; phase ^= 1; }
+            };
             for (int t = 0; t < n_tiles; ++t) {
+                const int np = __ldg(tile_planes + t);
                 for (int kc = 0; kc < k_chunks; ++kc) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t dst = smem_base + stage * stage_bytes;
-                    const uint32_t bar = full0 + 8 * stage;
-                    mbar_arrive_expect_tx(bar, stage_bytes);
-                    tma_load_2d(dst, &map_q, bar, kc * BK, int(q0));
-#pragma unroll
-                    for (int j = 0; j < n_planes; ++j)
-                        tma_load_2d(dst + (1 + j) * TILE_BYTES, &map_m, bar, kc * BK, j * ann_pad + t * BN);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (!RESIDENT) push(&map_q, kc * BK, int(q0));
+                    for (int j = 0; j < np; ++j) push(&map_m, kc * BK, j * ann_pad + t * BN);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int stage = 0;
+            int slot = 0;
             uint32_t phase = 0;
+            if (RESIDENT) { mbar_wait(qfull, 0); tc_fence_after(); }
             for (int t = 0; t < n_tiles; ++t) {
+                const int np = __ldg(tile_planes + t);
                 const int as = t % acc_stages;
                 const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
                 mbar_wait(tempty0 + 8 * as, aphase ^ 1);       // epilogue has drained this accumulator set
                 tc_fence_after();
                 for (int kc = 0; kc < k_chunks; ++kc) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * stage_bytes;
-#pragma unroll
-                    for (int j = 0; j < n_planes; ++j) {
-                        const uint32_t b_addr = a_addr + (1 + j) * TILE_BYTES;
+                    uint32_t a_addr = smem_base + kc * TILE_BYTES;
+                    int a_slot = -1;
+                    if (!RESIDENT) {
+                        mbar_wait(full0 + 8 * slot, phase);
+                        a_addr = ring_base + slot * TILE_BYTES;
+                        a_slot = slot;
+                        if (++slot == slots) { slot = 0; phase ^= 1; }
+                    }
+                    for (int j = 0; j < np; ++j) {
+                        mbar_wait(full0 + 8 * slot, phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = ring_base + slot * TILE_BYTES;
                         const uint32_t d = tmem_base + uint32_t(as * acc_cols + j * BN);
 #pragma unroll
                         for (int kk = 0; kk < BK / UK; ++kk)
                             umma_i8(d, smem_desc(a_addr + kk * UK), smem_desc(b_addr + kk * UK), IDESC, (kc | kk) ? 1u : 0u);
+                        umma_commit(empty0 + 8 * slot);         // slot free once these MMAs have read it
+                        if (++slot == slots) { slot = 0; phase ^= 1; }
                     }
-                    umma_commit(empty0 + 8 * stage);            // stage free once these MMAs have read it
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (a_slot >= 0) umma_commit(empty0 + 8 * a_slot);
                 }
                 umma_commit(tfull0 + 8 * as);                   // accumulators of tile t complete
             }
@@ -184,11 +213,14 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const double inv_qn = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
         Top2d best{0.0, 0.0, -1, -1};
         for (int t = 0; t < n_tiles; ++t) {
+            const int np = __ldg(tile_planes + t);
             const int as = t % acc_stages;
             const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
-            {   // 1 / ||m_a|| of this tile (double-buffered by tile parity)
+            {   // original index and 1 / ||m_a|| of this tile's rows (double-buffered by tile parity)
                 const int a = t * BN + et;
-                const double m2 = (a < n_ann) ? mnorm2[a] : 0.0;
+                const int orig = (a < n_ann) ? __ldg(perm + a) : -1;
+                const double m2 = (orig >= 0) ? mnorm2[orig] : 0.0;
+                s_orig[t & 1][et] = orig;
                 s_inv_mn[t & 1][et] = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -196,22 +228,22 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * acc_cols);
             for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[n_planes][16];
+                uint32_t r[MAXP][16];
 #pragma unroll
-                for (int j = 0; j < n_planes; ++j) tmem_ld16(lane_addr + uint32_t(j * BN + c0), r[j]);
+                for (int j = 0; j < MAXP; ++j)
+                    if (j < np) tmem_ld16(lane_addr + uint32_t(j * BN + c0), r[j]);      // np is warp-uniform
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int a = t * BN + c0 + i;
+                    const int orig = s_orig[t & 1][c0 + i];
                     int64_t dot = 0;
 #pragma unroll
-                    for (int j = n_planes - 1; j >= 0; --j) dot = (dot << 8) + int64_t(int32_t(r[j][i]));
+                    for (int j = MAXP - 1; j >= 0; --j)
+                        if (j < np) dot = (dot << 8) + int64_t(int32_t(r[j][i]));
                     const double s = double(dot) * (inv_qn * s_inv_mn[t & 1][c0 + i]);
-                    if (a < n_ann) {
-                        if (full && q < nq) full[q * int64_t(n_ann) + a] = s;
-                        // ascending scan with strict '>' keeps the lowest index among ties
-                        if (best.i1 < 0 || s > best.s1) { best.s2 = best.s1; best.i2 = best.i1; best.s1 = s; best.i1 = a; }
-                        else if (best.i2 < 0 || s > best.s2) { best.s2 = s; best.i2 = a; }
+                    if (orig >= 0) {
+                        if (full && q < nq) full[q * int64_t(n_ann) + orig] = s;
+                        top2d_push(best, s, orig);
                     }
                 }
             }
@@ -250,26 +282,35 @@ __global__ void __launch_bounds__(256) split_q_kernel(const int32_t *__restrict_
     }
     if (bad) atomicOr(flag, 1);
 }
-// M int64 [A, K] -> planes uint8 [n_planes, Apad, Kp]: digit j of M in base 256 (rows/cols beyond A, K are zero)
+// M int64 [A, K] -> planes uint8 [n_planes, Apad, Kp]: digit j (base 256) of row perm[a]; rows / columns beyond
+// A, K are zero
 __global__ void __launch_bounds__(256) split_m_kernel(const int64_t *__restrict__ M, int64_t A, int64_t K, int64_t Apad,
-                                                      int64_t Kp, int n_planes, uint8_t *__restrict__ out) {
+                                                      int64_t Kp, int n_planes, const int32_t *__restrict__ perm,
+                                                      uint8_t *__restrict__ out) {
     const int64_t total = Apad * Kp;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
         const int64_t a = i / Kp, c = i - a * Kp;
-        const uint64_t v = (a < A && c < K) ? uint64_t(__ldg(M + a * K + c)) : 0ull;
+        const uint64_t v = (a < A && c < K) ? uint64_t(__ldg(M + int64_t(__ldg(perm + a)) * K + c)) : 0ull;
         for (int j = 0; j < n_planes; ++j) out[(int64_t(j) * Apad + a) * Kp + c] = uint8_t(v >> (8 * j));
     }
 }
-__global__ void __launch_bounds__(256) max_i64_kernel(const int64_t *__restrict__ X, int64_t n, unsigned long long *__restrict__ out) {
-    unsigned long long m = 0;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t v = X[i];
-        const unsigned long long u = v < 0 ? ~0ull : (unsigned long long)v;     // negative counts are not representable
-        m = u > m ? u : m;
-    }
+// largest entry of every row (one warp per row); negative entries are not representable -> all-ones
+__global__ void __launch_bounds__(256) row_max_kernel(const int64_t *__restrict__ X, int64_t rows, int64_t cols,
+                                                      unsigned long long *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        unsigned long long m = 0;
+        for (int64_t c = lane; c < cols; c += 32) {
+            const int64_t v = X[r * cols + c];
+            const unsigned long long u = v < 0 ? ~0ull : (unsigned long long)v;
+            m = u > m ? u : m;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, m, o); m = x > m ? x : m; }
-    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, m, o); m = x > m ? x : m; }
+        if (lane == 0) out[r] = m;
+    }
 }
 
 static PFN_cuTensorMapEncodeTiled encode_fn() {
@@ -298,6 +339,8 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t Kp
 }
 
 static int64_t pad128(int64_t x) { return (x + 127) & ~int64_t(127); }
+// prepared-matrix blob: [perm int32 Apad | tile_planes int32 Apad/128 | pad to 1024] [planes MAXP x Apad x Kp]
+static size_t meta_bytes(int64_t Apad) { return (size_t(Apad) * 4 + size_t(Apad / 128) * 4 + 1023) & ~size_t(1023); }
 
 }  // namespace tc
 }  // namespace skm
@@ -306,8 +349,9 @@ extern "C" {
 
 size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K) {
     using namespace skm::tc;
-    if (n_ann <= 0 || K <= 0) return 256;
-    return size_t(MAX_PLANES) * size_t(pad128(n_ann)) * size_t(pad128(K)) + 256;
+    if (n_ann <= 0 || K <= 0) return 1024;
+    const int64_t Apad = pad128(n_ann);
+    return meta_bytes(Apad) + size_t(MAX_PLANES) * size_t(Apad) * size_t(pad128(K)) + 256;
 }
 
 int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes, size_t planes_bytes,
@@ -321,22 +365,39 @@ int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *
     if (!d_M || !d_planes || planes_bytes < skm_apply_tc_planes_bytes(n_ann, K)) { set_error("skm_apply_tc_prepare: bad buffers"); return SKM_ERR_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_planes) & 127u) != 0) { set_error("skm_apply_tc_prepare: d_planes must be 128-byte aligned"); return SKM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    // the largest entry decides the number of base-256 digit planes (uses the head of d_planes as scratch)
-    unsigned long long *d_max = reinterpret_cast<unsigned long long *>(d_planes);
-    SKM_CUDA_TRY(cudaMemsetAsync(d_max, 0, 8, st));
-    const int64_t n = n_ann * K;
-    max_i64_kernel<<<(int)std::min<int64_t>((n + 255) / 256, int64_t(sm_count()) * 8), 256, 0, st>>>(d_M, n, d_max);
-    SKM_LAUNCH_CHECK("max_i64_kernel");
-    unsigned long long h_max = 0;
-    SKM_CUDA_TRY(cudaMemcpyAsync(&h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    const int64_t Apad = pad128(n_ann), Kp = pad128(K), n_tiles = Apad / 128;
+    // per-row maxima decide the digit planes a row needs (the plane area of the blob is scratch until the split)
+    uint8_t *planes = d_planes + meta_bytes(Apad);
+    unsigned long long *d_rowmax = reinterpret_cast<unsigned long long *>(planes);
+    row_max_kernel<<<(int)std::min<int64_t>((n_ann + 7) / 8, int64_t(sm_count()) * 8), 256, 0, st>>>(d_M, n_ann, K, d_rowmax);
+    SKM_LAUNCH_CHECK("row_max_kernel");
+    std::vector<unsigned long long> rowmax((size_t)n_ann);
+    SKM_CUDA_TRY(cudaMemcpyAsync(rowmax.data(), d_rowmax, size_t(n_ann) * 8, cudaMemcpyDeviceToHost, st));
     SKM_CUDA_TRY(cudaStreamSynchronize(st));
-    int planes = 1;
-    while (planes < 8 && (h_max >> (8 * planes)) != 0) ++planes;
-    if (planes > MAX_PLANES) { set_error("skm_apply_tc_prepare: entries up to %llu need %d digit planes (> %d); use skm_apply_dense", h_max, planes, MAX_PLANES); return SKM_ERR_UNSUPPORTED; }
-    const int64_t Apad = pad128(n_ann), Kp = pad128(K);
-    split_m_kernel<<<(int)std::min<int64_t>((Apad * Kp + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_M, n_ann, K, Apad, Kp, planes, d_planes);
+    std::vector<int> cls((size_t)n_ann);
+    int max_planes = 1;
+    for (int64_t a = 0; a < n_ann; ++a) {
+        int p = 1;
+        while (p < 8 && (rowmax[a] >> (8 * p)) != 0) ++p;
+        cls[a] = p;
+        max_planes = std::max(max_planes, p);
+    }
+    if (max_planes > MAX_PLANES) { set_error("skm_apply_tc_prepare: entries need %d base-256 digit planes (> %d); use skm_apply_dense", max_planes, MAX_PLANES); return SKM_ERR_UNSUPPORTED; }
+    // rows sorted by class, largest first (stable: original order inside a class)
+    std::vector<int32_t> meta((size_t)Apad + (size_t)n_tiles, 0);
+    {
+        std::vector<int32_t> order((size_t)n_ann);
+        for (int64_t a = 0; a < n_ann; ++a) order[a] = (int32_t)a;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cls[x] > cls[y]; });
+        for (int64_t a = 0; a < n_ann; ++a) meta[a] = order[a];
+        for (int64_t t = 0; t < n_tiles; ++t) meta[Apad + t] = (t * 128 < n_ann) ? cls[order[t * 128]] : 1;
+    }
+    SKM_CUDA_TRY(cudaMemcpyAsync(d_planes, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
+    SKM_CUDA_TRY(cudaStreamSynchronize(st));          // `meta` is a local
+    split_m_kernel<<<(int)std::min<int64_t>((Apad * Kp + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(
+        d_M, n_ann, K, Apad, Kp, max_planes, reinterpret_cast<const int32_t *>(d_planes), planes);
     SKM_LAUNCH_CHECK("split_m_kernel");
-    *n_planes_out = planes;
+    *n_planes_out = max_planes;
     return SKM_OK;
 }
 
@@ -360,6 +421,9 @@ int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_pla
     if (!workspace || workspace_bytes < need) { set_error("skm_apply_tc: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t Kp = pad128(K), Apad = pad128(n_ann);
+    const int32_t *perm = reinterpret_cast<const int32_t *>(d_planes);
+    const int32_t *tile_planes = perm + Apad;
+    const uint8_t *planes = d_planes + meta_bytes(Apad);
     uint8_t *q8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     SKM_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     split_q_kernel<<<(int)std::min<int64_t>((nq * (Kp >> 2) + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_Q, nq, K, Kp, q8, d_status);
@@ -367,27 +431,32 @@ int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_pla
     alignas(64) CUtensorMap map_q, map_m;
     int rc = make_map(&map_q, q8, nq, Kp);
     if (rc) return rc;
-    rc = make_map(&map_m, d_planes, int64_t(n_planes) * Apad, Kp);
+    rc = make_map(&map_m, planes, int64_t(n_planes) * Apad, Kp);
     if (rc) return rc;
-    const uint32_t stage_bytes = uint32_t(1 + n_planes) * TILE_BYTES;
-    int stages = int((200 * 1024) / stage_bytes);
-    if (stages > 8) stages = 8;
-    if (stages < 2) { set_error("skm_apply_tc: pipeline does not fit shared memory"); return SKM_ERR_UNSUPPORTED; }
-    const size_t smem = size_t(stages) * stage_bytes + 1024;
+    const int k_chunks = int(Kp / BK);
+    const bool resident = k_chunks <= 8;                       // 128 queries x 1024 bytes = 128 KB of the 227 KB
+    const size_t budget = 227 * 1024 - 4096 - 1024;           // static shared + alignment slack
+    const size_t q_bytes = resident ? size_t(k_chunks) * TILE_BYTES : 0;
+    int slots = int((budget - q_bytes) / TILE_BYTES);
+    if (slots > 8) slots = 8;
+    if (slots < 2) { set_error("skm_apply_tc: pipeline does not fit shared memory"); return SKM_ERR_UNSUPPORTED; }
+    const size_t smem = q_bytes + size_t(slots) * TILE_BYTES + 1024;
     const unsigned grid = (unsigned)((nq + BM - 1) / BM);
-#define SKM_LAUNCH_TC(NP)                                                                                                    \
+#define SKM_LAUNCH_TC(NP, RES)                                                                                               \
     {                                                                                                                        \
-        auto kern = apply_tc_kernel<NP>;                                                                                     \
+        auto kern = apply_tc_kernel<NP, RES>;                                                                                \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        kern<<<grid, THREADS, smem, st>>>(map_q, map_m, (int)Apad, nq, (int)n_ann, (int)(Kp / BK), stages, d_qnorm2, d_mnorm2, \
-                                          d_top1, d_top2, d_score1, d_score2, d_scores_full);                                \
+        kern<<<grid, THREADS, smem, st>>>(map_q, map_m, (int)Apad, nq, (int)n_ann, k_chunks, slots, perm, tile_planes,       \
+                                          d_qnorm2, d_mnorm2, d_top1, d_top2, d_score1, d_score2, d_scores_full);            \
     }
+#define SKM_LAUNCH_TC_NP(NP) { if (resident) SKM_LAUNCH_TC(NP, true) else SKM_LAUNCH_TC(NP, false) }
     switch (n_planes) {
-        case 1: SKM_LAUNCH_TC(1) break;
-        case 2: SKM_LAUNCH_TC(2) break;
-        case 3: SKM_LAUNCH_TC(3) break;
-        default: SKM_LAUNCH_TC(4) break;
+        case 1: SKM_LAUNCH_TC_NP(1) break;
+        case 2: SKM_LAUNCH_TC_NP(2) break;
+        case 3: SKM_LAUNCH_TC_NP(3) break;
+        default: SKM_LAUNCH_TC_NP(4) break;
     }
+#undef SKM_LAUNCH_TC_NP
 #undef SKM_LAUNCH_TC
     SKM_LAUNCH_CHECK("apply_tc_kernel");
     return SKM_OK;
