@@ -14,9 +14,10 @@
 //               into a multi-stage shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer: one elected lane issues 4 x n_planes tcgen05.mma (M=128, N=128,
 //               K=32) per stage, tcgen05.commit releases the stage / publishes the tile
-//   warps 2-5   epilogue: tcgen05.ld the int32 accumulators (lane = query row), recombine the
-//               digits in int64, scale, keep a running top-2 per query in registers
-// TMEM: n_planes x 128 columns per accumulator set, double-buffered when it fits 512 columns.
+//   warps 2-5   epilogue: tcgen05.ld the int32 accumulators (lane = query row); float32 screening
+//               against the running runner-up, exact int64 / float64 path for the survivors,
+//               running top-2 per query in registers
+// TMEM: 4 accumulator slots of 128 columns; a tile takes one slot per digit plane (ring).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -30,6 +31,7 @@ namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 128, UK = 32;
 constexpr int MAX_PLANES = 4;
+constexpr int ACC_SLOTS = 4;                  // TMEM accumulator slots of BN columns
 constexpr int TILE_BYTES = BM * BK;            // 16 KB: one 128 x 128-byte operand tile
 constexpr int THREADS = 192;
 constexpr int64_t MAX_K = 32768;               // K * 255 * 255 < 2^31
@@ -79,12 +81,22 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+#define SKM_R4(a, o) "=r"(a[o]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3])
+// tcgen05.ld 32x32b: lane l of warp w reads TMEM lane 32*(w%4)+l, N consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : SKM_R4(r, 0) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : SKM_R4(r, 0), SKM_R4(r, 4), SKM_R4(r, 8), SKM_R4(r, 12) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : SKM_R4(r, 0), SKM_R4(r, 4), SKM_R4(r, 8), SKM_R4(r, 12), SKM_R4(r, 16), SKM_R4(r, 20), SKM_R4(r, 24), SKM_R4(r, 28)
                  : "r"(addr));
 }
+#undef SKM_R4
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart
@@ -105,12 +117,107 @@ __device__ __forceinline__ void top2d_push(Top2d &t, double s, int i) {
     else if (t.i2 < 0 || s > t.s2 || (s == t.s2 && i < t.i2)) { t.s2 = s; t.i2 = i; }
 }
 
+// per-tile epilogue operands staged in shared memory by the epilogue warps (double-buffered by tile parity)
+struct EpiTile {
+    double inv_mn[BN];      // 1 / ||m_a||  (0 for zero rows and padding)
+    float inv_m32[BN];      // the same in float: the screening pass
+    int32_t orig[BN];       // original annotation index, -1 = padding row
+};
+
+// exact dot of one (query, annotation) pair from its digit-plane accumulators
+template <int NP, int W>
+__device__ __forceinline__ int64_t plane_dot(const uint32_t (&r)[NP][W], int i) {
+    int64_t dot = 0;
+#pragma unroll
+    for (int j = NP - 1; j >= 0; --j) dot = (dot << 8) + int64_t(int32_t(r[j][i]));
+    return dot;
+}
+template <int NP, int W>
+__device__ __forceinline__ float plane_dot_f32(const uint32_t (&r)[NP][W], int i) {
+    float v = __int2float_rn(int32_t(r[NP - 1][i]));
+#pragma unroll
+    for (int j = NP - 2; j >= 0; --j) v = fmaf(v, 256.0f, __int2float_rn(int32_t(r[j][i])));
+    return v;
+}
+
+// Epilogue of one annotation tile WITHOUT the full score matrix.  The scores only feed a top-2, so every
+// accumulator is first screened in float32 — s32 = float(dot) / ||m|| against a threshold a little below the
+// running runner-up — and only survivors (~2 ln A per query) take the exact path: int64 dot, float64 scaling,
+// tie -> lowest index.  The screening keeps the float64 / 64-bit conversion (XU pipe, 16 lanes/clk) out of the
+// common path: the first version converted every accumulator and was bound by that pipe at 7 % tensor activity.
+// Zero dots never pass (thr > 0); the caller fills a missing runner-up with the lowest-index zero-score row.
+template <int NP>
+__device__ __forceinline__ void epi_tile_screen(uint32_t lane_addr, uint32_t cursor, const EpiTile &et, double inv_qn, double qn,
+                                                Top2d &best, float &thr) {
+    constexpr int CW = (NP == 1) ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CW) {
+        uint32_t r[NP][CW];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0, r[j]);
+        tmem_ld_wait();
+        uint32_t gm = 0;                                   // bit g: one of columns c0 + 4g .. 4g+3 may enter this query's top-2
+#pragma unroll
+        for (int i = 0; i < CW; i += 4) {
+            const float4 im = *reinterpret_cast<const float4 *>(&et.inv_m32[c0 + i]);
+            const float f0 = plane_dot_f32<NP, CW>(r, i) * im.x, f1 = plane_dot_f32<NP, CW>(r, i + 1) * im.y;
+            const float f2 = plane_dot_f32<NP, CW>(r, i + 2) * im.z, f3 = plane_dot_f32<NP, CW>(r, i + 3) * im.w;
+            if (fmaxf(fmaxf(f0, f1), fmaxf(f2, f3)) >= thr) gm |= 1u << (i >> 2);
+        }
+        uint32_t wm = __reduce_or_sync(FULL, gm);          // warp-uniform: groups some lane wants to look at
+        while (wm) {
+            const int g = __ffs(wm) - 1;
+            wm &= wm - 1;
+            uint32_t v[NP][4];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0 + 4 * g, v[j]);   // warp-collective re-read
+            tmem_ld_wait();
+            if ((gm >> g) & 1u) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = c0 + 4 * g + e;
+                    const int orig = et.orig[col];
+                    if (orig >= 0 && plane_dot_f32<NP, 4>(v, e) * et.inv_m32[col] >= thr)
+                        top2d_push(best, double(plane_dot<NP, 4>(v, e)) * (inv_qn * et.inv_mn[col]), orig);
+                }
+                // below the runner-up by more than the float32 error of the screening product (3 * 2^-24)
+                if (best.i2 >= 0) thr = fmaxf(thr, __double2float_rd(best.s2 * qn) * 0.99999f);
+            }
+        }
+    }
+}
+
+// Epilogue of one annotation tile WITH the full score matrix (save_apply_associations): every score is needed in
+// float64, so everything takes the exact path.
+template <int NP>
+__device__ __forceinline__ void epi_tile_full(uint32_t lane_addr, uint32_t cursor, const EpiTile &et, double inv_qn, Top2d &best,
+                                              double *__restrict__ full_row, bool q_ok) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[NP][16];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0, r[j]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int orig = et.orig[c0 + i];
+            const double s = double(plane_dot<NP, 16>(r, i)) * (inv_qn * et.inv_mn[c0 + i]);
+            if (orig >= 0) {
+                if (q_ok) full_row[orig] = s;
+                top2d_push(best, s, orig);
+            }
+        }
+    }
+}
+
 // Annotation rows are stored sorted by magnitude class (perm[sorted] = original index), so that a tile of 128
-// rows only carries the digit planes its largest entry needs (tile_planes[t] <= MAXP): small annotations — the
-// bulk of a Zipf-like family size distribution — cost one or two int8 GEMM passes instead of MAXP.
+// rows only carries the digit planes its largest entry needs (tile_planes[t] <= 4): small annotations — the
+// bulk of a Zipf-like family size distribution — cost one int8 GEMM pass instead of several.
+// TMEM: 512 columns = 4 accumulator slots of 128 columns; a tile with np planes takes np consecutive slots
+// (mod 4), so 1-plane tiles are 4 deep in flight and the epilogue of tile t overlaps the MMAs of t+1 .. t+3.
 // RESIDENT: the whole 128-query operand (k_chunks x 16 KB) stays in shared memory for the CTA's lifetime and
 // only annotation tiles stream through the ring (K <= 1024); otherwise query chunks travel through the ring too.
-template <int MAXP, bool RESIDENT>
+template <bool RESIDENT, bool FULLOUT>
 __global__ void __launch_bounds__(THREADS, 1)
 apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_m, int ann_pad,
                 int64_t nq, int n_ann, int k_chunks, int slots, const int32_t *__restrict__ perm,
@@ -118,23 +225,21 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const double *__restrict__ mnorm2, int32_t *__restrict__ top1, int32_t *__restrict__ top2,
                 double *__restrict__ sc1, double *__restrict__ sc2, double *__restrict__ full) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 1];   // full[8], empty[8], tmem_full[2], tmem_empty[2], q_full
+    __shared__ __align__(8) uint64_t bars[2 * 8 + 2 * ACC_SLOTS + 1];   // full[8], empty[8], tmem_full[4], tmem_empty[4], q_full
     __shared__ uint32_t s_tmem;
-    __shared__ double s_inv_mn[2][BN];
-    __shared__ int32_t s_orig[2][BN];
+    __shared__ __align__(16) EpiTile s_epi[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;
     const uint32_t q_bytes = RESIDENT ? uint32_t(k_chunks) * TILE_BYTES : 0u;
     const uint32_t ring_base = smem_base + q_bytes;
-    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[18]), qfull = s2u(&bars[20]);
-    constexpr int acc_stages = (MAXP * BN * 2 <= 512) ? 2 : 1;
-    constexpr int acc_cols = MAXP * BN;
-    constexpr uint32_t tmem_cols = (acc_cols * acc_stages <= 128) ? 128 : (acc_cols * acc_stages <= 256 ? 256 : 512);
+    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[16 + ACC_SLOTS]),
+                   qfull = s2u(&bars[16 + 2 * ACC_SLOTS]);
+    constexpr uint32_t tmem_cols = ACC_SLOTS * BN;          // 512: the whole TMEM of the SM (one CTA per SM)
     const int n_tiles = (n_ann + BN - 1) / BN;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < slots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
         mbar_init(qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -176,12 +281,15 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (lane == 0) {
             int slot = 0;
             uint32_t phase = 0;
+            uint32_t cursor = 0, par_empty = 0;                 // bit s of par_empty: parity of the uses of accumulator slot s so far
             if (RESIDENT) { mbar_wait(qfull, 0); tc_fence_after(); }
             for (int t = 0; t < n_tiles; ++t) {
                 const int np = __ldg(tile_planes + t);
-                const int as = t % acc_stages;
-                const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
-                mbar_wait(tempty0 + 8 * as, aphase ^ 1);       // epilogue has drained this accumulator set
+                for (int j = 0; j < np; ++j) {                  // the epilogue has drained the slots this tile takes
+                    const uint32_t s = (cursor + j) & 3u;
+                    mbar_wait(tempty0 + 8 * s, ((par_empty >> s) & 1u) ^ 1u);
+                    par_empty ^= 1u << s;
+                }
                 tc_fence_after();
                 for (int kc = 0; kc < k_chunks; ++kc) {
                     uint32_t a_addr = smem_base + kc * TILE_BYTES;
@@ -196,7 +304,7 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                         mbar_wait(full0 + 8 * slot, phase);
                         tc_fence_after();
                         const uint32_t b_addr = ring_base + slot * TILE_BYTES;
-                        const uint32_t d = tmem_base + uint32_t(as * acc_cols + j * BN);
+                        const uint32_t d = tmem_base + ((cursor + j) & 3u) * BN;
 #pragma unroll
                         for (int kk = 0; kk < BK / UK; ++kk)
                             umma_i8(d, smem_desc(a_addr + kk * UK), smem_desc(b_addr + kk * UK), IDESC, (kc | kk) ? 1u : 0u);
@@ -205,7 +313,8 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     }
                     if (a_slot >= 0) umma_commit(empty0 + 8 * a_slot);
                 }
-                umma_commit(tfull0 + 8 * as);                   // accumulators of tile t complete
+                umma_commit(tfull0 + 8 * cursor);               // accumulators of tile t complete (keyed by its first slot)
+                cursor = (cursor + np) & 3u;
             }
         }
     } else {
@@ -215,48 +324,54 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int64_t q = q0 + row;
         const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
         const double qn2 = (q < nq) ? qnorm2[q] : 0.0;
-        const double inv_qn = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
+        const double qn = sqrt(qn2);
+        const double inv_qn = qn2 > 0.0 ? 1.0 / qn : 0.0;
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
         Top2d best{0.0, 0.0, -1, -1};
+        float thr = 1e-30f;                                       // > 0: zero dots are never candidates (see the final fill)
+        uint32_t cursor = 0, par_full = 0;
         for (int t = 0; t < n_tiles; ++t) {
             const int np = __ldg(tile_planes + t);
-            const int as = t % acc_stages;
-            const uint32_t aphase = uint32_t(t / acc_stages) & 1u;
-            {   // original index and 1 / ||m_a|| of this tile's rows (double-buffered by tile parity)
+            EpiTile &tile = s_epi[t & 1];
+            {   // original index and 1 / ||m_a|| of this tile's rows
                 const int a = t * BN + et;
                 const int orig = (a < n_ann) ? __ldg(perm + a) : -1;
                 const double m2 = (orig >= 0) ? mnorm2[orig] : 0.0;
-                s_orig[t & 1][et] = orig;
-                s_inv_mn[t & 1][et] = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
+                const double inv = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
+                tile.orig[et] = orig;
+                tile.inv_mn[et] = inv;
+                tile.inv_m32[et] = float(inv);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(tfull0 + 8 * as, aphase);
+            mbar_wait(tfull0 + 8 * cursor, (par_full >> cursor) & 1u);
+            par_full ^= 1u << cursor;
             tc_fence_after();
-            const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(as * acc_cols);
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t r[MAXP][16];
-#pragma unroll
-                for (int j = 0; j < MAXP; ++j)
-                    if (j < np) tmem_ld16(lane_addr + uint32_t(j * BN + c0), r[j]);      // np is warp-uniform
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int orig = s_orig[t & 1][c0 + i];
-                    int64_t dot = 0;
-#pragma unroll
-                    for (int j = MAXP - 1; j >= 0; --j)
-                        if (j < np) dot = (dot << 8) + int64_t(int32_t(r[j][i]));
-                    const double s = double(dot) * (inv_qn * s_inv_mn[t & 1][c0 + i]);
-                    if (orig >= 0) {
-                        if (full && q < nq) full[q * int64_t(n_ann) + orig] = s;
-                        top2d_push(best, s, orig);
-                    }
+            if (FULLOUT) {
+                double *full_row = full + (q < nq ? q : 0) * int64_t(n_ann);
+                switch (np) {
+                    case 1: epi_tile_full<1>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
+                    case 2: epi_tile_full<2>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
+                    case 3: epi_tile_full<3>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
+                    default: epi_tile_full<4>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
+                }
+            } else {
+                switch (np) {
+                    case 1: epi_tile_screen<1>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
+                    case 2: epi_tile_screen<2>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
+                    case 3: epi_tile_screen<3>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
+                    default: epi_tile_screen<4>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
                 }
             }
             tc_fence_before();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * as);        // 4 arrivals (one per epilogue warp) free the set
+            if (lane == 0)
+                for (int j = 0; j < np; ++j) mbar_arrive(tempty0 + 8 * ((cursor + j) & 3u));   // 4 arrivals (one per warp) free a slot
+            cursor = (cursor + np) & 3u;
         }
         if (q < nq) {
-            top1[q] = best.i1; sc1[q] = best.i1 >= 0 ? best.s1 : 0.0;
+            // rows that were never candidates score exactly 0: a missing winner / runner-up is the lowest-index one of them
+            if (best.i1 < 0) { best.i1 = 0; best.s1 = 0.0; }
+            if (best.i2 < 0 && n_ann > 1) { best.i2 = (best.i1 == 0) ? 1 : 0; best.s2 = 0.0; }
+            top1[q] = best.i1; sc1[q] = best.s1;
             top2[q] = best.i2; sc2[q] = best.i2 >= 0 ? best.s2 : nan("");
         }
     }
@@ -440,28 +555,22 @@ int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_pla
     if (rc) return rc;
     const int k_chunks = int(Kp / BK);
     const bool resident = k_chunks <= 8;                       // 128 queries x 1024 bytes = 128 KB of the 227 KB
-    const size_t budget = 227 * 1024 - 4096 - 1024;           // static shared + alignment slack
+    const size_t budget = 227 * 1024 - 6144 - 1024;           // static shared (barriers + 2 epilogue tiles) + alignment slack
     const size_t q_bytes = resident ? size_t(k_chunks) * TILE_BYTES : 0;
     int slots = int((budget - q_bytes) / TILE_BYTES);
     if (slots > 8) slots = 8;
     if (slots < 2) { set_error("skm_apply_tc: pipeline does not fit shared memory"); return SKM_ERR_UNSUPPORTED; }
     const size_t smem = q_bytes + size_t(slots) * TILE_BYTES + 1024;
     const unsigned grid = (unsigned)((nq + BM - 1) / BM);
-#define SKM_LAUNCH_TC(NP, RES)                                                                                               \
+#define SKM_LAUNCH_TC(RES, FULLOUT)                                                                                          \
     {                                                                                                                        \
-        auto kern = apply_tc_kernel<NP, RES>;                                                                                \
+        auto kern = apply_tc_kernel<RES, FULLOUT>;                                                                           \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kern<<<grid, THREADS, smem, st>>>(map_q, map_m, (int)Apad, nq, (int)n_ann, k_chunks, slots, perm, tile_planes,       \
                                           d_qnorm2, d_mnorm2, d_top1, d_top2, d_score1, d_score2, d_scores_full);            \
     }
-#define SKM_LAUNCH_TC_NP(NP) { if (resident) SKM_LAUNCH_TC(NP, true) else SKM_LAUNCH_TC(NP, false) }
-    switch (n_planes) {
-        case 1: SKM_LAUNCH_TC_NP(1) break;
-        case 2: SKM_LAUNCH_TC_NP(2) break;
-        case 3: SKM_LAUNCH_TC_NP(3) break;
-        default: SKM_LAUNCH_TC_NP(4) break;
-    }
-#undef SKM_LAUNCH_TC_NP
+    if (resident) { if (d_scores_full) SKM_LAUNCH_TC(true, true) else SKM_LAUNCH_TC(true, false) }
+    else { if (d_scores_full) SKM_LAUNCH_TC(false, true) else SKM_LAUNCH_TC(false, false) }
 #undef SKM_LAUNCH_TC
     SKM_LAUNCH_CHECK("apply_tc_kernel");
     return SKM_OK;
