@@ -221,7 +221,7 @@ SKM_API int skm_apply_dense(const int32_t *d_Q, int64_t nq, int64_t K,
 SKM_API size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K);
 SKM_API int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes,
                          size_t planes_bytes, int *n_planes_out, skm_stream_t stream);
-SKM_API size_t skm_apply_tc_workspace(int64_t nq, int64_t K);
+SKM_API size_t skm_apply_tc_workspace(int64_t nq, int64_t K, int64_t n_ann);
 SKM_API int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_planes,
                  int n_planes, int64_t n_ann, const double *d_qnorm2,
                  const double *d_mnorm2, int32_t *d_top1, int32_t *d_top2,

@@ -20,9 +20,10 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 Q = torch.randint(0, 4, (a.nq, a.K), generator=g, device=dev, dtype=torch.int32)
 M = torch.randint(0, a.mmax + 1, (a.ann, a.K), generator=g, device=dev, dtype=torch.int64)
 prep = E.prepare_annotations(M)
-Apad = (a.ann + 127) // 128 * 128
-meta = prep.planes[: Apad * 4 + Apad // 128 * 4].view(torch.int32)
-tile_planes = meta[Apad:Apad + Apad // 128].cpu().numpy()
+hdr = prep.planes[:8].view(torch.int32).cpu().numpy()          # blob header: n_tiles, rows per plane
+n_tiles, rows = int(hdr[0]), int(hdr[1])
+toff = 1024 + rows * 4                                         # TileDesc {row0, width, np, pad} after the permutation
+tiles = prep.planes[toff:toff + 16 * n_tiles].view(torch.int32).cpu().numpy().reshape(-1, 4)
 qn2 = E.row_norm2(Q)
 for _ in range(2):
     r = E.apply_tc(Q, prep, qn2)
@@ -34,6 +35,6 @@ for _ in range(a.reps):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 Kp = (a.K + 127) // 128 * 128
-ops = 2.0 * a.nq * float(tile_planes.sum()) * 128 * Kp
-print(f"nq={a.nq} ann={a.ann} K={a.K} mmax={a.mmax} planes(max)={prep.n_planes} mean planes/tile={tile_planes.mean():.2f} "
+ops = 2.0 * a.nq * float((tiles[:, 1] * tiles[:, 2]).sum()) * Kp
+print(f"nq={a.nq} ann={a.ann} K={a.K} mmax={a.mmax} planes(max)={prep.n_planes} tiles={n_tiles} mean planes/tile={tiles[:, 2].mean():.2f} "
       f"ms={ms:.3f} TOP/s={ops / ms / 1e9:.1f}")

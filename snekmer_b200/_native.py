@@ -60,7 +60,7 @@ SIGNATURES = {
     "skm_apply_sparse": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "skm_apply_tc_planes_bytes": (_sz, [_i64, _i64]),
     "skm_apply_tc_prepare": (_int, [_p, _i64, _i64, _p, _sz, C.POINTER(_int), _p]),
-    "skm_apply_tc_workspace": (_sz, [_i64, _i64]),
+    "skm_apply_tc_workspace": (_sz, [_i64, _i64, _i64]),
     "skm_apply_tc": (_int, [_p, _i64, _i64, _p, _int, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_top2_merge": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "skm_row_norm2_i32": (_int, [_p, _i64, _i64, _p, _p]),

@@ -9,15 +9,18 @@
 //   M (annotation sums)       -> n_planes base-256 digits   B operands, K-major
 //   dot[q, a] = sum_j 256^j * (Q . M_j^T)[q, a]             exact while K * 255^2 < 2^31
 // and only the final scaling by 1 / (||q|| ||m||) is floating point (float64, like the
-// reference).  One CTA owns 128 queries and walks all annotation tiles of 128:
-//   warp 0      TMA producer: 128 x 128-byte boxes of Q and of every M plane (SWIZZLE_128B)
-//               into a multi-stage shared-memory ring, completion on mbarriers
-//   warp 1      MMA issuer: one elected lane issues 4 x n_planes tcgen05.mma (M=128, N=128,
-//               K=32) per stage, tcgen05.commit releases the stage / publishes the tile
+// reference).  A CTA PAIR (cluster of 2, cta_group::2) owns 256 queries and walks all annotation
+// tiles; per CTA:
+//   warp 0      TMA producer: this CTA's query rows, its HALF of every annotation tile
+//               (SWIZZLE_128B boxes) and the tile's epilogue operands into shared-memory rings,
+//               completion on mbarriers (the operand bytes of both CTAs land on the leader's)
+//   warp 1      MMA issuer (leader CTA): one elected lane issues 4 tcgen05.mma (M=256, N=256 or 128,
+//               K=32) per ring slot; tcgen05.commit (multicast) releases the slot / publishes the tile
 //   warps 2-5   epilogue: tcgen05.ld the int32 accumulators (lane = query row); float32 screening
 //               against the running runner-up, exact int64 / float64 path for the survivors,
 //               running top-2 per query in registers
-// TMEM: 4 accumulator slots of 128 columns; a tile takes one slot per digit plane (ring).
+// TMEM: two halves of 256 columns; a 1-plane tile of 256 annotations takes one half, so its epilogue
+// overlaps the MMAs of the next tile.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -29,15 +32,37 @@
 namespace skm {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 128, UK = 32;
+constexpr int BM = 128, BK = 128, UK = 32;     // query rows per CTA, bytes of K per ring slot, bytes of K per MMA
+constexpr int WIDE = 256, NARROW = 128;        // annotation rows per tile
 constexpr int MAX_PLANES = 4;
-constexpr int ACC_SLOTS = 4;                  // TMEM accumulator slots of BN columns
-constexpr int TILE_BYTES = BM * BK;            // 16 KB: one 128 x 128-byte operand tile
+constexpr int SLOT_BYTES = BM * BK;            // 16 KB: 128 rows x 128 bytes (query chunk, or a CTA's half of a wide tile)
+constexpr int MAX_SLOTS = 16;                  // ring slots (barrier arrays)
+constexpr int META_RING = 3;                   // tile-meta buffers in shared memory
 constexpr int THREADS = 192;
 constexpr int64_t MAX_K = 32768;               // K * 255 * 255 < 2^31
 
+// one annotation tile of the prepared matrix (rows in sorted order)
+struct TileDesc {
+    int32_t row0;       // first sorted row
+    int32_t width;      // WIDE or NARROW
+    int32_t np;         // digit planes this tile carries (1..4; WIDE tiles: 1..2)
+    int32_t pad;
+};
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp; the compiler then knows the guarded code runs on a single lane and issues the
+// uniform-datapath instructions (UTMALDG, UTCIMMA, UTCBAR) directly instead of a per-lane serialisation loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -63,21 +88,52 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+// 1-D bulk copy global -> this CTA's shared memory (16-byte aligned, size % 16 == 0), bytes complete on a local mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// ---- CTA pair (cluster of 2, cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope): the accumulator reads it orders are TMEM loads fenced by
+    // tcgen05.fence::before_thread_sync; a cluster-scope release costs a MEMBAR.GPU per arrival (12 % of the
+    // epilogue's time in the first pair version)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes complete on an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+// one MMA over both SMs of the pair: M = 256 (128 query rows from each CTA's shared memory), N annotation rows (N / 2
+// from each), D = 128 lanes x N columns in each CTA's TMEM.  Issued by the leader CTA (rank 0) only.
+template <bool ACCUMULATE>
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACCUMULATE ? 1 : 0) : "memory");
 }
-// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -85,6 +141,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // tcgen05.ld 32x32b: lane l of warp w reads TMEM lane 32*(w%4)+l, N consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : SKM_R4(r, 0) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : SKM_R4(r, 0), SKM_R4(r, 4) : "r"(addr));
 }
 __device__ __forceinline__ void tmem_ld(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -104,8 +163,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return uint64_t((addr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
            (uint64_t(2) << 61);
 }
-// kind::i8: D = S32, A = B = unsigned 8-bit, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+// kind::i8: D = S32, A = B = unsigned 8-bit, both K-major, M = 256 (the CTA pair), N = tile width
+constexpr uint32_t IDESC_WIDE = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(WIDE >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);
+constexpr uint32_t IDESC_NARROW = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(NARROW >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);
 
 struct Top2d {
     double s1, s2;
@@ -117,11 +177,20 @@ __device__ __forceinline__ void top2d_push(Top2d &t, double s, int i) {
     else if (t.i2 < 0 || s > t.s2 || (s == t.s2 && i < t.i2)) { t.s2 = s; t.i2 = i; }
 }
 
-// per-tile epilogue operands staged in shared memory by the epilogue warps (double-buffered by tile parity)
+// Per-tile epilogue operands ("tile meta"), precomputed per call by tile_meta_kernel in the layout the epilogue reads
+// them in, one contiguous block per tile so that the producer brings it in with ONE bulk copy:
+//   [inv_mn float64 x width | inv_m32 float x width | orig int32 x width | inv_g8 float x width/8]
+// = 16.5 bytes per row; the block of the tile starting at sorted row row0 sits at byte row0 * 16.5.
+__host__ __device__ constexpr size_t meta_block_bytes(int width) { return size_t(width) * 16 + size_t(width) / 2; }
+__host__ __device__ constexpr size_t meta_block_offset(int64_t row0) { return size_t(row0) * 16 + size_t(row0) / 2; }
 struct EpiTile {
-    double inv_mn[BN];      // 1 / ||m_a||  (0 for zero rows and padding)
-    float inv_m32[BN];      // the same in float: the screening pass
-    int32_t orig[BN];       // original annotation index, -1 = padding row
+    const double *inv_mn;      // 1 / ||m_a||, 0 for zero rows and padding
+    const float *inv_m32;      // the same in float: the screening pass
+    const int32_t *orig;       // original annotation index, -1 = padding row
+    const float *inv_g8;       // largest inv_m32 of every group of 8 rows (rows of a class are sorted by norm: nearly equal)
+    __device__ __forceinline__ EpiTile(const uint8_t *base, int width)
+        : inv_mn(reinterpret_cast<const double *>(base)), inv_m32(reinterpret_cast<const float *>(base + 8 * width)),
+          orig(reinterpret_cast<const int32_t *>(base + 12 * width)), inv_g8(reinterpret_cast<const float *>(base + 16 * width)) {}
 };
 
 // exact dot of one (query, annotation) pair from its digit-plane accumulators
@@ -140,45 +209,57 @@ __device__ __forceinline__ float plane_dot_f32(const uint32_t (&r)[NP][W], int i
     return v;
 }
 
-// Epilogue of one annotation tile WITHOUT the full score matrix.  The scores only feed a top-2, so every
-// accumulator is first screened in float32 — s32 = float(dot) / ||m|| against a threshold a little below the
-// running runner-up — and only survivors (~2 ln A per query) take the exact path: int64 dot, float64 scaling,
-// tie -> lowest index.  The screening keeps the float64 / 64-bit conversion (XU pipe, 16 lanes/clk) out of the
-// common path: the first version converted every accumulator and was bound by that pipe at 7 % tensor activity.
+// Epilogue of one annotation tile WITHOUT the full score matrix.  The scores only feed a top-2, so the accumulators
+// are first screened in float32 against a threshold a little below the running runner-up, and only survivors
+// (~2 ln A per query) take the exact path: int64 dot, float64 scaling, tie -> lowest index.  1-plane tiles screen
+// 8 accumulators with ONE conversion: max(dot) * max(1/||m||) bounds every score of the group from above
+// (int -> float conversions run on the 16-lane XU pipe; one per accumulator made that pipe the limiter).
 // Zero dots never pass (thr > 0); the caller fills a missing runner-up with the lowest-index zero-score row.
+// tmem = this thread's TMEM lane address + first column of the tile; plane j starts `pstride` columns further.
 template <int NP>
-__device__ __forceinline__ void epi_tile_screen(uint32_t lane_addr, uint32_t cursor, const EpiTile &et, double inv_qn, double qn,
-                                                Top2d &best, float &thr) {
-    constexpr int CW = (NP == 1) ? 32 : 16;
+__device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride, int width, const EpiTile &et, double inv_qn,
+                                                double qn, Top2d &best, float &thr) {
+    constexpr int CW = (NP == 1) ? 32 : 16;       // columns per TMEM load
+    constexpr int GW = (NP == 1) ? 8 : 4;         // columns per screening group
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CW) {
+    for (int c0 = 0; c0 < width; c0 += CW) {
         uint32_t r[NP][CW];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0, r[j]);
+        for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0, r[j]);
         tmem_ld_wait();
-        uint32_t gm = 0;                                   // bit g: one of columns c0 + 4g .. 4g+3 may enter this query's top-2
+        uint32_t gm = 0;                                   // bit g: a column of group g may enter this query's top-2
+        if constexpr (NP == 1) {
 #pragma unroll
-        for (int i = 0; i < CW; i += 4) {
-            const float4 im = *reinterpret_cast<const float4 *>(&et.inv_m32[c0 + i]);
-            const float f0 = plane_dot_f32<NP, CW>(r, i) * im.x, f1 = plane_dot_f32<NP, CW>(r, i + 1) * im.y;
-            const float f2 = plane_dot_f32<NP, CW>(r, i + 2) * im.z, f3 = plane_dot_f32<NP, CW>(r, i + 3) * im.w;
-            if (fmaxf(fmaxf(f0, f1), fmaxf(f2, f3)) >= thr) gm |= 1u << (i >> 2);
+            for (int g = 0; g < CW / 8; ++g) {
+                const int i = 8 * g;
+                const int m = max(max(max(int(r[0][i]), int(r[0][i + 1])), max(int(r[0][i + 2]), int(r[0][i + 3]))),
+                                  max(max(int(r[0][i + 4]), int(r[0][i + 5])), max(int(r[0][i + 6]), int(r[0][i + 7]))));
+                if (__int2float_ru(m) * et.inv_g8[(c0 >> 3) + g] >= thr) gm |= 1u << g;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CW; i += 4) {
+                const float4 im = *reinterpret_cast<const float4 *>(&et.inv_m32[c0 + i]);
+                const float f0 = plane_dot_f32<NP, CW>(r, i) * im.x, f1 = plane_dot_f32<NP, CW>(r, i + 1) * im.y;
+                const float f2 = plane_dot_f32<NP, CW>(r, i + 2) * im.z, f3 = plane_dot_f32<NP, CW>(r, i + 3) * im.w;
+                if (fmaxf(fmaxf(f0, f1), fmaxf(f2, f3)) >= thr) gm |= 1u << (i >> 2);
+            }
         }
         uint32_t wm = __reduce_or_sync(FULL, gm);          // warp-uniform: groups some lane wants to look at
         while (wm) {
             const int g = __ffs(wm) - 1;
             wm &= wm - 1;
-            uint32_t v[NP][4];
+            uint32_t v[NP][GW];
 #pragma unroll
-            for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0 + 4 * g, v[j]);   // warp-collective re-read
+            for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0 + GW * g, v[j]);   // warp-collective re-read
             tmem_ld_wait();
             if ((gm >> g) & 1u) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int col = c0 + 4 * g + e;
+                for (int e = 0; e < GW; ++e) {
+                    const int col = c0 + GW * g + e;
                     const int orig = et.orig[col];
-                    if (orig >= 0 && plane_dot_f32<NP, 4>(v, e) * et.inv_m32[col] >= thr)
-                        top2d_push(best, double(plane_dot<NP, 4>(v, e)) * (inv_qn * et.inv_mn[col]), orig);
+                    if (orig >= 0 && plane_dot_f32<NP, GW>(v, e) * et.inv_m32[col] >= thr)
+                        top2d_push(best, double(plane_dot<NP, GW>(v, e)) * (inv_qn * et.inv_mn[col]), orig);
                 }
                 // below the runner-up by more than the float32 error of the screening product (3 * 2^-24)
                 if (best.i2 >= 0) thr = fmaxf(thr, __double2float_rd(best.s2 * qn) * 0.99999f);
@@ -190,13 +271,13 @@ __device__ __forceinline__ void epi_tile_screen(uint32_t lane_addr, uint32_t cur
 // Epilogue of one annotation tile WITH the full score matrix (save_apply_associations): every score is needed in
 // float64, so everything takes the exact path.
 template <int NP>
-__device__ __forceinline__ void epi_tile_full(uint32_t lane_addr, uint32_t cursor, const EpiTile &et, double inv_qn, Top2d &best,
-                                              double *__restrict__ full_row, bool q_ok) {
+__device__ __forceinline__ void epi_tile_full(uint32_t tmem, uint32_t pstride, int width, const EpiTile &et, double inv_qn,
+                                              Top2d &best, double *__restrict__ full_row, bool q_ok) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = 0; c0 < width; c0 += 16) {
         uint32_t r[NP][16];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) tmem_ld(lane_addr + ((cursor + j) & 3u) * BN + c0, r[j]);
+        for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0, r[j]);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -210,162 +291,220 @@ __device__ __forceinline__ void epi_tile_full(uint32_t lane_addr, uint32_t curso
     }
 }
 
-// Annotation rows are stored sorted by magnitude class (perm[sorted] = original index), so that a tile of 128
-// rows only carries the digit planes its largest entry needs (tile_planes[t] <= 4): small annotations — the
-// bulk of a Zipf-like family size distribution — cost one int8 GEMM pass instead of several.
-// TMEM: 512 columns = 4 accumulator slots of 128 columns; a tile with np planes takes np consecutive slots
-// (mod 4), so 1-plane tiles are 4 deep in flight and the epilogue of tile t overlaps the MMAs of t+1 .. t+3.
-// RESIDENT: the whole 128-query operand (k_chunks x 16 KB) stays in shared memory for the CTA's lifetime and
-// only annotation tiles stream through the ring (K <= 1024); otherwise query chunks travel through the ring too.
+// Annotation rows are stored sorted by magnitude class, so that a tile only carries the digit planes its largest entry
+// needs: the few rows with entries >= 2^16 form NARROW tiles (128 rows, 3-4 planes), everything else WIDE tiles
+// (256 rows, 1-2 planes) — small annotations, the bulk of a Zipf-like family size distribution, cost one int8 GEMM pass.
+//
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns 256 queries: each CTA keeps its 128 query rows and the
+// accumulators of those rows, and loads only HALF of every annotation tile; the MMA (M = 256, N = tile width),
+// issued by the leader CTA, reads both halves from both SMs.  That is 32 bytes of operand per SM and tensor-core
+// cycle, and 128 tensor cycles per instruction (N = 256), which one issuing lane can sustain; the first versions
+// (one CTA per tile, N = 128) sat at 39 % tensor activity, bound first by the L2 -> SM latency x bandwidth the ring
+// could cover and then by the issue rate of the MMA lane.
+// TMEM: 512 columns = two halves of 256; a 1-plane WIDE tile takes one half (its epilogue overlaps the next tile's
+// MMAs), every other tile takes both (plane j at column j * width).
+// RESIDENT: the CTA's whole 128-query operand (k_chunks x 16 KB) stays in shared memory for the CTA's lifetime and
+// only annotation half-tiles stream through the ring (K <= 1024); otherwise query chunks travel through the ring too.
+// Barriers: full[s] (leader only; bytes of both CTAs' loads), empty[s] (each CTA; multicast commit), tfull[h]
+// (each CTA; multicast commit), tempty[h] (leader only; 4 epilogue warps x 2 CTAs), mfull / mempty[b] (each CTA;
+// tile-meta ring between the producer and the 4 epilogue warps, which therefore never wait for one another).
 template <bool RESIDENT, bool FULLOUT>
-__global__ void __launch_bounds__(THREADS, 1)
-apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_m, int ann_pad,
-                int64_t nq, int n_ann, int k_chunks, int slots, const int32_t *__restrict__ perm,
-                const int32_t *__restrict__ tile_planes, const double *__restrict__ qnorm2,
-                const double *__restrict__ mnorm2, int32_t *__restrict__ top1, int32_t *__restrict__ top2,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_wide,
+                const __grid_constant__ CUtensorMap map_narrow, int plane_rows, int64_t nq, int n_ann, int k_chunks, int slots,
+                const uint8_t *__restrict__ tile_meta, const int32_t *__restrict__ header, const TileDesc *__restrict__ tiles,
+                const double *__restrict__ qnorm2, int32_t *__restrict__ top1, int32_t *__restrict__ top2,
                 double *__restrict__ sc1, double *__restrict__ sc2, double *__restrict__ full) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * 8 + 2 * ACC_SLOTS + 1];   // full[8], empty[8], tmem_full[4], tmem_empty[4], q_full
+    // full, empty, tmem_full[2], tmem_empty[2], q_full, meta_full, meta_empty
+    __shared__ __align__(8) uint64_t bars[2 * MAX_SLOTS + 2 * 2 + 1 + 2 * META_RING];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(16) EpiTile s_epi[2];
+    __shared__ __align__(128) uint8_t s_meta[META_RING][meta_block_bytes(WIDE)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;
-    const uint32_t q_bytes = RESIDENT ? uint32_t(k_chunks) * TILE_BYTES : 0u;
+    const uint32_t rank = cluster_ctarank();                  // 0 = leader
+    const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;   // same offset in both CTAs (same kernel, same layout)
+    const uint32_t q_bytes = RESIDENT ? uint32_t(k_chunks) * SLOT_BYTES : 0u;
     const uint32_t ring_base = smem_base + q_bytes;
-    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[8]), tfull0 = s2u(&bars[16]), tempty0 = s2u(&bars[16 + ACC_SLOTS]),
-                   qfull = s2u(&bars[16 + 2 * ACC_SLOTS]);
-    constexpr uint32_t tmem_cols = ACC_SLOTS * BN;          // 512: the whole TMEM of the SM (one CTA per SM)
-    const int n_tiles = (n_ann + BN - 1) / BN;
+    const uint32_t full0 = s2u(&bars[0]), empty0 = s2u(&bars[MAX_SLOTS]), tfull0 = s2u(&bars[2 * MAX_SLOTS]),
+                   tempty0 = s2u(&bars[2 * MAX_SLOTS + 2]), qfull = s2u(&bars[2 * MAX_SLOTS + 4]),
+                   mfull0 = s2u(&bars[2 * MAX_SLOTS + 5]), mempty0 = s2u(&bars[2 * MAX_SLOTS + 5 + META_RING]);
+    constexpr uint32_t tmem_cols = 512;                     // the whole TMEM of the SM (one CTA per SM)
+    const int n_tiles = __ldg(header);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < slots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         mbar_init(qfull, 1);
+        for (int i = 0; i < META_RING; ++i) { mbar_init(mfull0 + 8 * i, 1); mbar_init(mempty0 + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {        // TMEM allocation (whole warp), same warp frees it
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&s_tmem)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {        // TMEM allocation for the pair: one warp of each CTA, the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();     // the peer's barriers are initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    const int64_t q0 = int64_t(blockIdx.x) * BM;
+    const int64_t q0 = (int64_t(blockIdx.x >> 1) * 2 + rank) * BM;       // this CTA's 128 queries
+
+    // TMEM halves a tile takes: [half, half + nh); a 2-half tile starts at half 0 (a free half 1 is skipped)
+    auto tile_halves = [](const TileDesc &td, uint32_t &half) -> uint32_t {
+        const uint32_t nh = (td.width == WIDE && td.np == 1) ? 1u : 2u;
+        if (nh == 2u) half = 0u;
+        return nh;
+    };
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            if (RESIDENT) {
-                mbar_arrive_expect_tx(qfull, q_bytes);
-                for (int kc = 0; kc < k_chunks; ++kc) tma_load_2d(smem_base + kc * TILE_BYTES, &map_q, qfull, kc * BK, int(q0));
+        // ===== TMA producer (both CTAs): own query rows, own half of every annotation tile; bytes land on the LEADER's barriers.
+        // The whole warp walks the loop (waits are warp-uniform); one elected lane issues. =====
+        const uint32_t qfull_leader = mapa_rank(qfull, 0);
+        const uint32_t full0_leader = mapa_rank(full0, 0);
+        if (RESIDENT) {
+            if (elect_one()) {
+                if (rank == 0) mbar_arrive_expect_tx(qfull, 2 * q_bytes);
+                for (int kc = 0; kc < k_chunks; ++kc) tma_load_2d_pair(smem_base + kc * SLOT_BYTES, &map_q, qfull_leader, kc * BK, int(q0));
             }
-            int slot = 0;
-            uint32_t phase = 0;
-            auto push = [&](const CUtensorMap *map, int c0, int c1) {
-                mbar_wait(empty0 + 8 * slot, phase ^ 1);
-                mbar_arrive_expect_tx(full0 + 8 * slot, TILE_BYTES);
-                tma_load_2d(ring_base + slot * TILE_BYTES, map, full0 + 8 * slot, c0, c1);
-                if (++slot == slots) { slot = 0; phase ^= 1; }
-            };
-            for (int t = 0; t < n_tiles; ++t) {
-                const int np = __ldg(tile_planes + t);
-                for (int kc = 0; kc < k_chunks; ++kc) {
-                    if (!RESIDENT) push(&map_q, kc * BK, int(q0));
-                    for (int j = 0; j < np; ++j) push(&map_m, kc * BK, j * ann_pad + t * BN);
-                }
+            __syncwarp();
+        }
+        int slot = 0;
+        uint32_t phase = 0;
+        auto push = [&](const CUtensorMap *map, int c0, int c1, uint32_t bytes) {
+            mbar_wait(empty0 + 8 * slot, phase ^ 1);
+            if (elect_one()) {
+                if (rank == 0) mbar_arrive_expect_tx(full0 + 8 * slot, 2 * bytes);
+                tma_load_2d_pair(ring_base + slot * SLOT_BYTES, map, full0_leader + 8 * slot, c0, c1);
+            }
+            __syncwarp();
+            if (++slot == slots) { slot = 0; phase ^= 1; }
+        };
+        int mbuf = 0;
+        uint32_t mphase = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const TileDesc td = tiles[t];
+            const CUtensorMap *map = td.width == WIDE ? &map_wide : &map_narrow;
+            const int half_rows = td.width / 2;
+            // this tile's epilogue operands: one bulk copy into the next tile-meta buffer (each CTA keeps its own copy)
+            mbar_wait(mempty0 + 8 * mbuf, mphase ^ 1);
+            if (elect_one()) {
+                const uint32_t bytes = uint32_t(meta_block_bytes(td.width));
+                mbar_arrive_expect_tx(mfull0 + 8 * mbuf, bytes);
+                bulk_load(s2u(&s_meta[mbuf][0]), tile_meta + meta_block_offset(td.row0), bytes, mfull0 + 8 * mbuf);
+            }
+            __syncwarp();
+            if (++mbuf == META_RING) { mbuf = 0; mphase ^= 1; }
+            for (int kc = 0; kc < k_chunks; ++kc) {
+                if (!RESIDENT) push(&map_q, kc * BK, int(q0), SLOT_BYTES);
+                for (int j = 0; j < td.np; ++j) push(map, kc * BK, j * plane_rows + td.row0 + int(rank) * half_rows, uint32_t(half_rows) * BK);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (leader CTA only): the whole warp walks the loop, one elected lane issues.  Descriptors differ
+        // only in their 14-bit start-address field, so an operand K-step is one add on a precomputed descriptor. =====
+        if (rank == 0) {
             int slot = 0;
             uint32_t phase = 0;
-            uint32_t cursor = 0, par_empty = 0;                 // bit s of par_empty: parity of the uses of accumulator slot s so far
+            uint32_t half = 0, par_empty = 0;                   // bit h of par_empty: parity of the uses of TMEM half h so far
+            const uint64_t desc_q0 = smem_desc(smem_base), desc_ring0 = smem_desc(ring_base);
+            constexpr uint64_t slot_step = SLOT_BYTES >> 4, k_step = UK >> 4;
             if (RESIDENT) { mbar_wait(qfull, 0); tc_fence_after(); }
             for (int t = 0; t < n_tiles; ++t) {
-                const int np = __ldg(tile_planes + t);
-                for (int j = 0; j < np; ++j) {                  // the epilogue has drained the slots this tile takes
-                    const uint32_t s = (cursor + j) & 3u;
-                    mbar_wait(tempty0 + 8 * s, ((par_empty >> s) & 1u) ^ 1u);
-                    par_empty ^= 1u << s;
+                const TileDesc td = tiles[t];
+                const uint32_t nh = tile_halves(td, half);
+                for (uint32_t h = half; h < half + nh; ++h) {   // both CTAs' epilogues have drained the halves this tile takes
+                    mbar_wait(tempty0 + 8 * h, ((par_empty >> h) & 1u) ^ 1u);
+                    par_empty ^= 1u << h;
                 }
                 tc_fence_after();
+                const uint32_t idesc = td.width == WIDE ? IDESC_WIDE : IDESC_NARROW;
+                const uint32_t d0 = tmem_base + half * WIDE;
                 for (int kc = 0; kc < k_chunks; ++kc) {
-                    uint32_t a_addr = smem_base + kc * TILE_BYTES;
+                    uint64_t a_desc = desc_q0 + uint64_t(kc) * slot_step;
                     int a_slot = -1;
                     if (!RESIDENT) {
                         mbar_wait(full0 + 8 * slot, phase);
-                        a_addr = ring_base + slot * TILE_BYTES;
+                        a_desc = desc_ring0 + uint64_t(slot) * slot_step;
                         a_slot = slot;
                         if (++slot == slots) { slot = 0; phase ^= 1; }
                     }
-                    for (int j = 0; j < np; ++j) {
+                    for (int j = 0; j < td.np; ++j) {
                         mbar_wait(full0 + 8 * slot, phase);
                         tc_fence_after();
-                        const uint32_t b_addr = ring_base + slot * TILE_BYTES;
-                        const uint32_t d = tmem_base + ((cursor + j) & 3u) * BN;
+                        if (elect_one()) {
+                            const uint64_t b_desc = desc_ring0 + uint64_t(slot) * slot_step;
+                            const uint32_t d = d0 + uint32_t(j * td.width);
+                            if (kc == 0) {
+                                umma_i8_pair<false>(d, a_desc, b_desc, idesc);
+                            } else {
+                                umma_i8_pair<true>(d, a_desc, b_desc, idesc);
+                            }
 #pragma unroll
-                        for (int kk = 0; kk < BK / UK; ++kk)
-                            umma_i8(d, smem_desc(a_addr + kk * UK), smem_desc(b_addr + kk * UK), IDESC, (kc | kk) ? 1u : 0u);
-                        umma_commit(empty0 + 8 * slot);         // slot free once these MMAs have read it
+                            for (int kk = 1; kk < BK / UK; ++kk) umma_i8_pair<true>(d, a_desc + kk * k_step, b_desc + kk * k_step, idesc);
+                            umma_commit_pair(empty0 + 8 * slot);    // slot free in both CTAs once these MMAs have read it
+                        }
+                        __syncwarp();
                         if (++slot == slots) { slot = 0; phase ^= 1; }
                     }
-                    if (a_slot >= 0) umma_commit(empty0 + 8 * a_slot);
+                    if (a_slot >= 0) {
+                        if (elect_one()) umma_commit_pair(empty0 + 8 * a_slot);
+                        __syncwarp();
+                    }
                 }
-                umma_commit(tfull0 + 8 * cursor);               // accumulators of tile t complete (keyed by its first slot)
-                cursor = (cursor + np) & 3u;
+                if (elect_one()) umma_commit_pair(tfull0 + 8 * half);       // accumulators of tile t complete (keyed by its first half)
+                __syncwarp();
+                half = (half + nh) & 1u;
             }
         }
     } else {
-        // ===== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue (both CTAs): 4 warps, TMEM lane quarter = warp % 4; the warps run independently =====
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int64_t q = q0 + row;
-        const int et = threadIdx.x - 64;                          // 0..127 among the epilogue threads
         const double qn2 = (q < nq) ? qnorm2[q] : 0.0;
         const double qn = sqrt(qn2);
         const double inv_qn = qn2 > 0.0 ? 1.0 / qn : 0.0;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+        const uint32_t tempty_leader = mapa_rank(tempty0, 0);
         Top2d best{0.0, 0.0, -1, -1};
         float thr = 1e-30f;                                       // > 0: zero dots are never candidates (see the final fill)
-        uint32_t cursor = 0, par_full = 0;
+        uint32_t half = 0, par_full = 0;
+        int mbuf = 0;
+        uint32_t mphase = 0;
         for (int t = 0; t < n_tiles; ++t) {
-            const int np = __ldg(tile_planes + t);
-            EpiTile &tile = s_epi[t & 1];
-            {   // original index and 1 / ||m_a|| of this tile's rows
-                const int a = t * BN + et;
-                const int orig = (a < n_ann) ? __ldg(perm + a) : -1;
-                const double m2 = (orig >= 0) ? mnorm2[orig] : 0.0;
-                const double inv = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
-                tile.orig[et] = orig;
-                tile.inv_mn[et] = inv;
-                tile.inv_m32[et] = float(inv);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(tfull0 + 8 * cursor, (par_full >> cursor) & 1u);
-            par_full ^= 1u << cursor;
+            const TileDesc td = tiles[t];
+            mbar_wait(mfull0 + 8 * mbuf, mphase);                  // the producer's bulk copy of this tile's meta has landed
+            const EpiTile tile(&s_meta[mbuf][0], td.width);
+            const uint32_t nh = tile_halves(td, half);
+            mbar_wait(tfull0 + 8 * half, (par_full >> half) & 1u);
+            par_full ^= 1u << half;
             tc_fence_after();
+            const uint32_t tmem = lane_addr + half * WIDE;
+            const uint32_t pstride = uint32_t(td.width);
             if (FULLOUT) {
                 double *full_row = full + (q < nq ? q : 0) * int64_t(n_ann);
-                switch (np) {
-                    case 1: epi_tile_full<1>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
-                    case 2: epi_tile_full<2>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
-                    case 3: epi_tile_full<3>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
-                    default: epi_tile_full<4>(lane_addr, cursor, tile, inv_qn, best, full_row, q < nq); break;
+                switch (td.np) {
+                    case 1: epi_tile_full<1>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
+                    case 2: epi_tile_full<2>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
+                    case 3: epi_tile_full<3>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
+                    default: epi_tile_full<4>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
                 }
             } else {
-                switch (np) {
-                    case 1: epi_tile_screen<1>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
-                    case 2: epi_tile_screen<2>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
-                    case 3: epi_tile_screen<3>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
-                    default: epi_tile_screen<4>(lane_addr, cursor, tile, inv_qn, qn, best, thr); break;
+                switch (td.np) {
+                    case 1: epi_tile_screen<1>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
+                    case 2: epi_tile_screen<2>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
+                    case 3: epi_tile_screen<3>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
+                    default: epi_tile_screen<4>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
                 }
             }
             tc_fence_before();
-            if (lane == 0)
-                for (int j = 0; j < np; ++j) mbar_arrive(tempty0 + 8 * ((cursor + j) & 3u));   // 4 arrivals (one per warp) free a slot
-            cursor = (cursor + np) & 3u;
+            __syncwarp();
+            if (lane == 0) {
+                for (uint32_t h = half; h < half + nh; ++h) mbar_arrive_cluster(tempty_leader + 8 * h);   // 8 arrivals free a half
+                mbar_arrive(mempty0 + 8 * mbuf);                                                          // 4 arrivals free the meta buffer
+            }
+            if (++mbuf == META_RING) { mbuf = 0; mphase ^= 1; }
+            half = (half + nh) & 1u;
         }
         if (q < nq) {
             // rows that were never candidates score exactly 0: a missing winner / runner-up is the lowest-index one of them
@@ -377,10 +516,34 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrivals may still touch it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
+}
+
+// tile meta (see EpiTile): one block of 256 threads per tile
+__global__ void __launch_bounds__(WIDE) tile_meta_kernel(const int32_t *__restrict__ header, const TileDesc *__restrict__ tiles,
+                                                         const int32_t *__restrict__ perm, const double *__restrict__ mnorm2,
+                                                         uint8_t *__restrict__ out) {
+    if (int(blockIdx.x) >= __ldg(header)) return;
+    const TileDesc td = tiles[blockIdx.x];
+    const int i = threadIdx.x;
+    if (i >= td.width) return;                                   // whole warps (width is 128 or 256)
+    uint8_t *base = out + meta_block_offset(td.row0);
+    const int32_t orig = perm[td.row0 + i];
+    const double m2 = (orig >= 0) ? mnorm2[orig] : 0.0;
+    const double inv = m2 > 0.0 ? 1.0 / sqrt(m2) : 0.0;
+    const float inv32 = float(inv);
+    reinterpret_cast<double *>(base)[i] = inv;
+    reinterpret_cast<float *>(base + 8 * td.width)[i] = inv32;
+    reinterpret_cast<int32_t *>(base + 12 * td.width)[i] = orig;
+    float g8 = inv32;
+    g8 = fmaxf(g8, __shfl_xor_sync(FULL, g8, 1));
+    g8 = fmaxf(g8, __shfl_xor_sync(FULL, g8, 2));
+    g8 = fmaxf(g8, __shfl_xor_sync(FULL, g8, 4));
+    if ((i & 7) == 0) reinterpret_cast<float *>(base + 16 * td.width)[i >> 3] = g8;
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
@@ -402,34 +565,40 @@ __global__ void __launch_bounds__(256) split_q_kernel(const int32_t *__restrict_
     }
     if (bad) atomicOr(flag, 1);
 }
-// M int64 [A, K] -> planes uint8 [n_planes, Apad, Kp]: digit j (base 256) of row perm[a]; rows / columns beyond
-// A, K are zero
-__global__ void __launch_bounds__(256) split_m_kernel(const int64_t *__restrict__ M, int64_t A, int64_t K, int64_t Apad,
-                                                      int64_t Kp, int n_planes, const int32_t *__restrict__ perm,
-                                                      uint8_t *__restrict__ out) {
-    const int64_t total = Apad * Kp;
+// M int64 [A, K] -> planes uint8 [n_planes, rows, Kp]: digit j (base 256) of row perm[a]; padding rows (perm < 0) and
+// columns beyond K are zero
+__global__ void __launch_bounds__(256) split_m_kernel(const int64_t *__restrict__ M, int64_t K, int64_t rows, int64_t Kp,
+                                                      int n_planes, const int32_t *__restrict__ perm, uint8_t *__restrict__ out) {
+    const int64_t total = rows * Kp;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
         const int64_t a = i / Kp, c = i - a * Kp;
-        const uint64_t v = (a < A && c < K) ? uint64_t(__ldg(M + int64_t(__ldg(perm + a)) * K + c)) : 0ull;
-        for (int j = 0; j < n_planes; ++j) out[(int64_t(j) * Apad + a) * Kp + c] = uint8_t(v >> (8 * j));
+        const int32_t o = __ldg(perm + a);
+        const uint64_t v = (o >= 0 && c < K) ? uint64_t(__ldg(M + int64_t(o) * K + c)) : 0ull;
+        for (int j = 0; j < n_planes; ++j) out[(int64_t(j) * rows + a) * Kp + c] = uint8_t(v >> (8 * j));
     }
 }
-// largest entry of every row (one warp per row); negative entries are not representable -> all-ones
+// largest entry (negative entries are not representable -> all-ones) and squared norm of every row, one warp per row
 __global__ void __launch_bounds__(256) row_max_kernel(const int64_t *__restrict__ X, int64_t rows, int64_t cols,
-                                                      unsigned long long *__restrict__ out) {
+                                                      unsigned long long *__restrict__ out, double *__restrict__ norm2) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     for (int64_t r = warp; r < rows; r += nwarps) {
         unsigned long long m = 0;
+        double n2 = 0.0;
         for (int64_t c = lane; c < cols; c += 32) {
             const int64_t v = X[r * cols + c];
             const unsigned long long u = v < 0 ? ~0ull : (unsigned long long)v;
             m = u > m ? u : m;
+            n2 += double(v) * double(v);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, m, o); m = x > m ? x : m; }
-        if (lane == 0) out[r] = m;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long x = __shfl_xor_sync(FULL, m, o);
+            m = x > m ? x : m;
+            n2 += __shfl_xor_sync(FULL, n2, o);
+        }
+        if (lane == 0) { out[r] = m; norm2[r] = n2; }
     }
 }
 
@@ -443,13 +612,13 @@ static PFN_cuTensorMapEncodeTiled encode_fn() {
     }
     return fn;
 }
-// uint8 matrix [rows, Kp] row-major, boxes of 128 rows x 128 bytes, 128-byte swizzle, zero fill outside
-static int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t Kp) {
+// uint8 matrix [rows, Kp] row-major, boxes of box_rows rows x 128 bytes, 128-byte swizzle, zero fill outside
+static int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t Kp, int box_rows) {
     PFN_cuTensorMapEncodeTiled fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SKM_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Kp};
-    cuuint32_t box[2] = {BK, BM};
+    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -459,8 +628,13 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int64_t Kp
 }
 
 static int64_t pad128(int64_t x) { return (x + 127) & ~int64_t(127); }
-// prepared-matrix blob: [perm int32 Apad | tile_planes int32 Apad/128 | pad to 1024] [planes MAXP x Apad x Kp]
-static size_t meta_bytes(int64_t Apad) { return (size_t(Apad) * 4 + size_t(Apad / 128) * 4 + 1023) & ~size_t(1023); }
+// rows of the prepared matrix: the narrow region is padded to 128, the wide region to 256
+static int64_t plane_rows_for(int64_t n_ann) { return pad128(n_ann + 127 + 255); }
+// prepared-matrix blob: [header 1024 B: n_tiles, plane_rows | perm int32 rows | TileDesc rows/128 | pad to 1024]
+//                       [planes MAX_PLANES x rows x Kp]
+static size_t perm_offset() { return 1024; }
+static size_t tiles_offset(int64_t rows) { return perm_offset() + size_t(rows) * 4; }
+static size_t meta_bytes(int64_t rows) { return (tiles_offset(rows) + size_t(rows / 128) * sizeof(TileDesc) + 1023) & ~size_t(1023); }
 
 }  // namespace tc
 }  // namespace skm
@@ -469,9 +643,9 @@ extern "C" {
 
 size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K) {
     using namespace skm::tc;
-    if (n_ann <= 0 || K <= 0) return 1024;
-    const int64_t Apad = pad128(n_ann);
-    return meta_bytes(Apad) + size_t(MAX_PLANES) * size_t(Apad) * size_t(pad128(K)) + 256;
+    if (n_ann <= 0 || K <= 0) return 2048;
+    const int64_t rows = plane_rows_for(n_ann);
+    return meta_bytes(rows) + size_t(MAX_PLANES) * size_t(rows) * size_t(pad128(K)) + 256;
 }
 
 int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes, size_t planes_bytes,
@@ -482,49 +656,66 @@ int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *
     *n_planes_out = 0;
     if (n_ann <= 0 || K <= 0) { set_error("skm_apply_tc_prepare: empty matrix"); return SKM_ERR_INVALID; }
     if (K > MAX_K) { set_error("skm_apply_tc_prepare: K=%lld > %lld (int32 accumulators would overflow); use skm_apply_dense", (long long)K, (long long)MAX_K); return SKM_ERR_UNSUPPORTED; }
+    if (n_ann > 0x7FFFF000ll) { set_error("skm_apply_tc_prepare: too many annotations"); return SKM_ERR_UNSUPPORTED; }
     if (!d_M || !d_planes || planes_bytes < skm_apply_tc_planes_bytes(n_ann, K)) { set_error("skm_apply_tc_prepare: bad buffers"); return SKM_ERR_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_planes) & 127u) != 0) { set_error("skm_apply_tc_prepare: d_planes must be 128-byte aligned"); return SKM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t Apad = pad128(n_ann), Kp = pad128(K), n_tiles = Apad / 128;
+    const int64_t rows = plane_rows_for(n_ann), Kp = pad128(K);
     // per-row maxima decide the digit planes a row needs (the plane area of the blob is scratch until the split)
-    uint8_t *planes = d_planes + meta_bytes(Apad);
+    uint8_t *planes = d_planes + meta_bytes(rows);
     unsigned long long *d_rowmax = reinterpret_cast<unsigned long long *>(planes);
-    row_max_kernel<<<(int)std::min<int64_t>((n_ann + 7) / 8, int64_t(sm_count()) * 8), 256, 0, st>>>(d_M, n_ann, K, d_rowmax);
+    double *d_rownorm2 = reinterpret_cast<double *>(d_rowmax + n_ann);
+    row_max_kernel<<<(int)std::min<int64_t>((n_ann + 7) / 8, int64_t(sm_count()) * 8), 256, 0, st>>>(d_M, n_ann, K, d_rowmax, d_rownorm2);
     SKM_LAUNCH_CHECK("row_max_kernel");
     std::vector<unsigned long long> rowmax((size_t)n_ann);
+    std::vector<double> rownorm2((size_t)n_ann);
     SKM_CUDA_TRY(cudaMemcpyAsync(rowmax.data(), d_rowmax, size_t(n_ann) * 8, cudaMemcpyDeviceToHost, st));
+    SKM_CUDA_TRY(cudaMemcpyAsync(rownorm2.data(), d_rownorm2, size_t(n_ann) * 8, cudaMemcpyDeviceToHost, st));
     SKM_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<int> cls((size_t)n_ann);
     int max_planes = 1;
+    int64_t n_narrow = 0;
     for (int64_t a = 0; a < n_ann; ++a) {
         int p = 1;
         while (p < 8 && (rowmax[a] >> (8 * p)) != 0) ++p;
         cls[a] = p;
         max_planes = std::max(max_planes, p);
+        n_narrow += p > 2;
     }
     if (max_planes > MAX_PLANES) { set_error("skm_apply_tc_prepare: entries need %d base-256 digit planes (> %d); use skm_apply_dense", max_planes, MAX_PLANES); return SKM_ERR_UNSUPPORTED; }
-    // rows sorted by class, largest first (stable: original order inside a class)
-    std::vector<int32_t> meta((size_t)Apad + (size_t)n_tiles, 0);
-    {
-        std::vector<int32_t> order((size_t)n_ann);
-        for (int64_t a = 0; a < n_ann; ++a) order[a] = (int32_t)a;
-        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cls[x] > cls[y]; });
-        for (int64_t a = 0; a < n_ann; ++a) meta[a] = order[a];
-        for (int64_t t = 0; t < n_tiles; ++t) meta[Apad + t] = (t * 128 < n_ann) ? cls[order[t * 128]] : 1;
-    }
+    // rows sorted by class, largest first, and by norm inside a class: neighbouring rows then have nearly equal norms,
+    // which is what lets the epilogue screen 8 accumulators with one bound (epi_tile_screen).  Classes 3-4 (entries
+    // >= 2^16) form the narrow region, classes 1-2 the wide region.
+    std::vector<int32_t> order((size_t)n_ann);
+    for (int64_t a = 0; a < n_ann; ++a) order[a] = (int32_t)a;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return cls[x] != cls[y] ? cls[x] > cls[y] : rownorm2[x] > rownorm2[y];
+    });
+    const int64_t narrow_rows = pad128(n_narrow), n_wide = n_ann - n_narrow;
+    std::vector<int32_t> meta(meta_bytes(rows) / 4, 0);
+    int32_t *perm = meta.data() + perm_offset() / 4;
+    TileDesc *tiles = reinterpret_cast<TileDesc *>(meta.data() + tiles_offset(rows) / 4);
+    for (int64_t r = 0; r < rows; ++r) perm[r] = -1;
+    for (int64_t i = 0; i < n_narrow; ++i) perm[i] = order[i];
+    for (int64_t i = 0; i < n_wide; ++i) perm[narrow_rows + i] = order[n_narrow + i];
+    int32_t n_tiles = 0;
+    for (int64_t r0 = 0; r0 < n_narrow; r0 += NARROW) tiles[n_tiles++] = TileDesc{(int32_t)r0, NARROW, cls[perm[r0]], 0};
+    for (int64_t r0 = 0; r0 < n_wide; r0 += WIDE) tiles[n_tiles++] = TileDesc{(int32_t)(narrow_rows + r0), WIDE, cls[perm[narrow_rows + r0]], 0};
+    meta[0] = n_tiles;
+    meta[1] = (int32_t)rows;
     SKM_CUDA_TRY(cudaMemcpyAsync(d_planes, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, st));
     SKM_CUDA_TRY(cudaStreamSynchronize(st));          // `meta` is a local
-    split_m_kernel<<<(int)std::min<int64_t>((Apad * Kp + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(
-        d_M, n_ann, K, Apad, Kp, max_planes, reinterpret_cast<const int32_t *>(d_planes), planes);
+    split_m_kernel<<<(int)std::min<int64_t>((rows * Kp + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(
+        d_M, K, rows, Kp, max_planes, reinterpret_cast<const int32_t *>(d_planes + perm_offset()), planes);
     SKM_LAUNCH_CHECK("split_m_kernel");
     *n_planes_out = max_planes;
     return SKM_OK;
 }
 
-size_t skm_apply_tc_workspace(int64_t nq, int64_t K) {
+size_t skm_apply_tc_workspace(int64_t nq, int64_t K, int64_t n_ann) {
     using namespace skm::tc;
-    if (nq <= 0 || K <= 0) return 512;
-    return size_t(nq) * size_t(pad128(K)) + 512;
+    if (nq <= 0 || K <= 0 || n_ann <= 0) return 512;
+    return size_t(nq) * size_t(pad128(K)) + meta_block_offset(plane_rows_for(n_ann)) + 1024;
 }
 
 int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_planes, int n_planes, int64_t n_ann,
@@ -533,41 +724,48 @@ int skm_apply_tc(const int32_t *d_Q, int64_t nq, int64_t K, const uint8_t *d_pla
                  skm_stream_t stream) {
     using namespace skm;
     using namespace skm::tc;
-    if (nq < 0 || K <= 0 || K > MAX_K || n_ann <= 0 || n_ann > 0x7FFFFF00ll || n_planes < 1 || n_planes > MAX_PLANES) { set_error("skm_apply_tc: bad sizes (K=%lld n_ann=%lld planes=%d)", (long long)K, (long long)n_ann, n_planes); return SKM_ERR_INVALID; }
+    if (nq < 0 || K <= 0 || K > MAX_K || n_ann <= 0 || n_ann > 0x7FFFF000ll || n_planes < 1 || n_planes > MAX_PLANES) { set_error("skm_apply_tc: bad sizes (K=%lld n_ann=%lld planes=%d)", (long long)K, (long long)n_ann, n_planes); return SKM_ERR_INVALID; }
     if (nq == 0) return SKM_OK;
     if (nq > 0x7FFFFF00ll) { set_error("skm_apply_tc: more than 2^31 queries per call"); return SKM_ERR_UNSUPPORTED; }
     if (!d_Q || !d_planes || !d_qnorm2 || !d_mnorm2 || !d_top1 || !d_top2 || !d_score1 || !d_score2 || !d_status) { set_error("skm_apply_tc: NULL argument"); return SKM_ERR_INVALID; }
-    const size_t need = skm_apply_tc_workspace(nq, K);
+    const size_t need = skm_apply_tc_workspace(nq, K, n_ann);
     if (!workspace || workspace_bytes < need) { set_error("skm_apply_tc: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t Kp = pad128(K), Apad = pad128(n_ann);
-    const int32_t *perm = reinterpret_cast<const int32_t *>(d_planes);
-    const int32_t *tile_planes = perm + Apad;
-    const uint8_t *planes = d_planes + meta_bytes(Apad);
-    uint8_t *q8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const int64_t Kp = pad128(K), rows = plane_rows_for(n_ann);
+    const int32_t *header = reinterpret_cast<const int32_t *>(d_planes);
+    const int32_t *perm = reinterpret_cast<const int32_t *>(d_planes + perm_offset());
+    const TileDesc *tiles = reinterpret_cast<const TileDesc *>(d_planes + tiles_offset(rows));
+    const uint8_t *planes = d_planes + meta_bytes(rows);
+    uint8_t *tile_meta = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    uint8_t *q8 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tile_meta + meta_block_offset(rows)) + 255) & ~uintptr_t(255));
     SKM_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    tile_meta_kernel<<<(unsigned)(rows / NARROW), WIDE, 0, st>>>(header, tiles, perm, d_mnorm2, tile_meta);
+    SKM_LAUNCH_CHECK("tile_meta_kernel");
     split_q_kernel<<<(int)std::min<int64_t>((nq * (Kp >> 2) + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_Q, nq, K, Kp, q8, d_status);
     SKM_LAUNCH_CHECK("split_q_kernel");
-    alignas(64) CUtensorMap map_q, map_m;
-    int rc = make_map(&map_q, q8, nq, Kp);
+    alignas(64) CUtensorMap map_q, map_wide, map_narrow;
+    int rc = make_map(&map_q, q8, nq, Kp, BM);
     if (rc) return rc;
-    rc = make_map(&map_m, planes, int64_t(n_planes) * Apad, Kp);
+    rc = make_map(&map_wide, planes, int64_t(n_planes) * rows, Kp, WIDE / 2);
+    if (rc) return rc;
+    rc = make_map(&map_narrow, planes, int64_t(n_planes) * rows, Kp, NARROW / 2);
     if (rc) return rc;
     const int k_chunks = int(Kp / BK);
     const bool resident = k_chunks <= 8;                       // 128 queries x 1024 bytes = 128 KB of the 227 KB
-    const size_t budget = 227 * 1024 - 6144 - 1024;           // static shared (barriers + 2 epilogue tiles) + alignment slack
-    const size_t q_bytes = resident ? size_t(k_chunks) * TILE_BYTES : 0;
-    int slots = int((budget - q_bytes) / TILE_BYTES);
-    if (slots > 8) slots = 8;
+    const size_t budget = 227 * 1024 - 14336 - 1024;          // static shared (barriers + tile-meta ring) + alignment slack
+    const size_t q_bytes = resident ? size_t(k_chunks) * SLOT_BYTES : 0;
+    int slots = int((budget - q_bytes) / SLOT_BYTES);
+    if (slots > MAX_SLOTS) slots = MAX_SLOTS;
     if (slots < 2) { set_error("skm_apply_tc: pipeline does not fit shared memory"); return SKM_ERR_UNSUPPORTED; }
-    const size_t smem = q_bytes + size_t(slots) * TILE_BYTES + 1024;
-    const unsigned grid = (unsigned)((nq + BM - 1) / BM);
+    // > half of the SM's shared memory: one CTA per SM, which the 512-column TMEM allocation relies on
+    const size_t smem = std::max<size_t>(q_bytes + size_t(slots) * SLOT_BYTES + 1024, 120 * 1024);
+    const unsigned grid = 2u * (unsigned)((nq + 2 * BM - 1) / (2 * BM));          // CTA pairs of 256 queries
 #define SKM_LAUNCH_TC(RES, FULLOUT)                                                                                          \
     {                                                                                                                        \
         auto kern = apply_tc_kernel<RES, FULLOUT>;                                                                           \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        kern<<<grid, THREADS, smem, st>>>(map_q, map_m, (int)Apad, nq, (int)n_ann, k_chunks, slots, perm, tile_planes,       \
-                                          d_qnorm2, d_mnorm2, d_top1, d_top2, d_score1, d_score2, d_scores_full);            \
+        kern<<<grid, THREADS, smem, st>>>(map_q, map_wide, map_narrow, (int)rows, nq, (int)n_ann, k_chunks, slots, tile_meta, \
+                                          header, tiles, d_qnorm2, d_top1, d_top2, d_score1, d_score2, d_scores_full);       \
     }
     if (resident) { if (d_scores_full) SKM_LAUNCH_TC(true, true) else SKM_LAUNCH_TC(true, false) }
     else { if (d_scores_full) SKM_LAUNCH_TC(false, true) else SKM_LAUNCH_TC(false, false) }

@@ -527,7 +527,7 @@ def apply_tc(Q: torch.Tensor, prep: PreparedAnnotations, qnorm2: Optional[torch.
     s2 = torch.empty(nq, dtype=torch.float64, device=dev)
     scores = torch.empty((nq, A), dtype=torch.float64, device=dev) if full else None
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws_bytes = lib().skm_apply_tc_workspace(nq, K)
+    ws_bytes = lib().skm_apply_tc_workspace(nq, K, A)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib().skm_apply_tc(_ptr(Q), nq, K, _ptr(prep.planes), prep.n_planes, A, _ptr(qnorm2), _ptr(prep.mnorm2), _ptr(top1),
                              _ptr(top2), _ptr(s1), _ptr(s2), _ptr(scores), _ptr(status), _ptr(ws), ws_bytes, _stream()))
