@@ -254,12 +254,24 @@ __device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride,
             for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0 + GW * g, v[j]);   // warp-collective re-read
             tmem_ld_wait();
             if ((gm >> g) & 1u) {
+                uint32_t pm = 0;                           // columns of the group that pass the float32 screen
 #pragma unroll
-                for (int e = 0; e < GW; ++e) {
+                for (int e = 0; e < GW; ++e)
+                    if (plane_dot_f32<NP, GW>(v, e) * et.inv_m32[c0 + GW * g + e] >= thr) pm |= 1u << e;
+                while (pm) {                               // usually one: ONE copy of the exact path, operands picked by select chains
+                    const int e = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    int64_t dot = 0;
+#pragma unroll
+                    for (int j = NP - 1; j >= 0; --j) {
+                        uint32_t x = v[j][0];
+#pragma unroll
+                        for (int i = 1; i < GW; ++i) x = (e == i) ? v[j][i] : x;
+                        dot = (dot << 8) + int64_t(int32_t(x));
+                    }
                     const int col = c0 + GW * g + e;
                     const int orig = et.orig[col];
-                    if (orig >= 0 && plane_dot_f32<NP, GW>(v, e) * et.inv_m32[col] >= thr)
-                        top2d_push(best, double(plane_dot<NP, GW>(v, e)) * (inv_qn * et.inv_mn[col]), orig);
+                    if (orig >= 0) top2d_push(best, double(dot) * (inv_qn * et.inv_mn[col]), orig);
                 }
                 // below the runner-up by more than the float32 error of the screening product (3 * 2^-24)
                 if (best.i2 >= 0) thr = fmaxf(thr, __double2float_rd(best.s2 * qn) * 0.99999f);
