@@ -16,9 +16,10 @@
 //               completion on mbarriers (the operand bytes of both CTAs land on the leader's)
 //   warp 1      MMA issuer (leader CTA): one elected lane issues 4 tcgen05.mma (M=256, N=256 or 128,
 //               K=32) per ring slot; tcgen05.commit (multicast) releases the slot / publishes the tile
-//   warps 2-5   epilogue: tcgen05.ld the int32 accumulators (lane = query row); float32 screening
-//               against the running runner-up, exact int64 / float64 path for the survivors,
-//               running top-2 per query in registers
+//   warps 2-9   epilogue: tcgen05.ld the int32 accumulators (lane = query row; two warps per TMEM
+//               lane quarter, each on half of the tile's columns); float32 screening against the
+//               running runner-up, exact int64 / float64 path for the survivors, running top-2 per
+//               query in registers, merged at the end
 // TMEM: two halves of 256 columns; a 1-plane tile of 256 annotations takes one half, so its epilogue
 // overlaps the MMAs of the next tile.
 #include <cuda.h>
@@ -38,7 +39,8 @@ constexpr int MAX_PLANES = 4;
 constexpr int SLOT_BYTES = BM * BK;            // 16 KB: 128 rows x 128 bytes (query chunk, or a CTA's half of a wide tile)
 constexpr int MAX_SLOTS = 16;                  // ring slots (barrier arrays)
 constexpr int META_RING = 3;                   // tile-meta buffers in shared memory
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter: each takes half of a tile's columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int64_t MAX_K = 32768;               // K * 255 * 255 < 2^31
 
 // one annotation tile of the prepared matrix (rows in sorted order)
@@ -217,12 +219,12 @@ __device__ __forceinline__ float plane_dot_f32(const uint32_t (&r)[NP][W], int i
 // Zero dots never pass (thr > 0); the caller fills a missing runner-up with the lowest-index zero-score row.
 // tmem = this thread's TMEM lane address + first column of the tile; plane j starts `pstride` columns further.
 template <int NP>
-__device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride, int width, const EpiTile &et, double inv_qn,
+__device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride, int cbeg, int cend, const EpiTile &et, double inv_qn,
                                                 double qn, Top2d &best, float &thr) {
     constexpr int CW = (NP == 1) ? 32 : 16;       // columns per TMEM load
     constexpr int GW = (NP == 1) ? 8 : 4;         // columns per screening group
 #pragma unroll 1
-    for (int c0 = 0; c0 < width; c0 += CW) {
+    for (int c0 = cbeg; c0 < cend; c0 += CW) {
         uint32_t r[NP][CW];
 #pragma unroll
         for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0, r[j]);
@@ -283,10 +285,10 @@ __device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride,
 // Epilogue of one annotation tile WITH the full score matrix (save_apply_associations): every score is needed in
 // float64, so everything takes the exact path.
 template <int NP>
-__device__ __forceinline__ void epi_tile_full(uint32_t tmem, uint32_t pstride, int width, const EpiTile &et, double inv_qn,
+__device__ __forceinline__ void epi_tile_full(uint32_t tmem, uint32_t pstride, int cbeg, int cend, const EpiTile &et, double inv_qn,
                                               Top2d &best, double *__restrict__ full_row, bool q_ok) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < width; c0 += 16) {
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
         uint32_t r[NP][16];
 #pragma unroll
         for (int j = 0; j < NP; ++j) tmem_ld(tmem + j * pstride + c0, r[j]);
@@ -318,8 +320,8 @@ __device__ __forceinline__ void epi_tile_full(uint32_t tmem, uint32_t pstride, i
 // RESIDENT: the CTA's whole 128-query operand (k_chunks x 16 KB) stays in shared memory for the CTA's lifetime and
 // only annotation half-tiles stream through the ring (K <= 1024); otherwise query chunks travel through the ring too.
 // Barriers: full[s] (leader only; bytes of both CTAs' loads), empty[s] (each CTA; multicast commit), tfull[h]
-// (each CTA; multicast commit), tempty[h] (leader only; 4 epilogue warps x 2 CTAs), mfull / mempty[b] (each CTA;
-// tile-meta ring between the producer and the 4 epilogue warps, which therefore never wait for one another).
+// (each CTA; multicast commit), tempty[h] (leader only; 8 epilogue warps x 2 CTAs), mfull / mempty[b] (each CTA;
+// tile-meta ring between the producer and the 8 epilogue warps, which therefore never wait for one another).
 template <bool RESIDENT, bool FULLOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_wide,
@@ -332,6 +334,7 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     __shared__ __align__(8) uint64_t bars[2 * MAX_SLOTS + 2 * 2 + 1 + 2 * META_RING];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(128) uint8_t s_meta[META_RING][meta_block_bytes(WIDE)];
+    __shared__ float s_thr[2][BM];                           // screening thresholds, exchanged between the two warps of a query row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();                  // 0 = leader
     const uint32_t smem_base = (s2u(smem) + 1023u) & ~1023u;   // same offset in both CTAs (same kernel, same layout)
@@ -345,9 +348,9 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < slots; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * EPI_WARPS); }
         mbar_init(qfull, 1);
-        for (int i = 0; i < META_RING; ++i) { mbar_init(mfull0 + 8 * i, 1); mbar_init(mempty0 + 8 * i, 4); }
+        for (int i = 0; i < META_RING; ++i) { mbar_init(mfull0 + 8 * i, 1); mbar_init(mempty0 + 8 * i, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // TMEM allocation for the pair: one warp of each CTA, the same warp frees it
@@ -469,8 +472,10 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
         }
     } else {
-        // ===== epilogue (both CTAs): 4 warps, TMEM lane quarter = warp % 4; the warps run independently =====
+        // ===== epilogue (both CTAs): 8 warps, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; the warps run
+        // independently.  The two warps of a row only share their screening thresholds (a bound from either half holds). =====
         const int quarter = warp & 3;
+        const int ch = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const int64_t q = q0 + row;
         const double qn2 = (q < nq) ? qnorm2[q] : 0.0;
@@ -480,6 +485,9 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t tempty_leader = mapa_rank(tempty0, 0);
         Top2d best{0.0, 0.0, -1, -1};
         float thr = 1e-30f;                                       // > 0: zero dots are never candidates (see the final fill)
+        volatile float *my_thr = &s_thr[ch][row], *other_thr = &s_thr[ch ^ 1][row];
+        *my_thr = thr;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         uint32_t half = 0, par_full = 0;
         int mbuf = 0;
         uint32_t mphase = 0;
@@ -493,32 +501,45 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_after();
             const uint32_t tmem = lane_addr + half * WIDE;
             const uint32_t pstride = uint32_t(td.width);
+            const int cbeg = ch * (td.width >> 1), cend = cbeg + (td.width >> 1);
+            *my_thr = thr;
+            thr = fmaxf(thr, *other_thr);
             if (FULLOUT) {
                 double *full_row = full + (q < nq ? q : 0) * int64_t(n_ann);
                 switch (td.np) {
-                    case 1: epi_tile_full<1>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
-                    case 2: epi_tile_full<2>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
-                    case 3: epi_tile_full<3>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
-                    default: epi_tile_full<4>(tmem, pstride, td.width, tile, inv_qn, best, full_row, q < nq); break;
+                    case 1: epi_tile_full<1>(tmem, pstride, cbeg, cend, tile, inv_qn, best, full_row, q < nq); break;
+                    case 2: epi_tile_full<2>(tmem, pstride, cbeg, cend, tile, inv_qn, best, full_row, q < nq); break;
+                    case 3: epi_tile_full<3>(tmem, pstride, cbeg, cend, tile, inv_qn, best, full_row, q < nq); break;
+                    default: epi_tile_full<4>(tmem, pstride, cbeg, cend, tile, inv_qn, best, full_row, q < nq); break;
                 }
             } else {
                 switch (td.np) {
-                    case 1: epi_tile_screen<1>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
-                    case 2: epi_tile_screen<2>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
-                    case 3: epi_tile_screen<3>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
-                    default: epi_tile_screen<4>(tmem, pstride, td.width, tile, inv_qn, qn, best, thr); break;
+                    case 1: epi_tile_screen<1>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
+                    case 2: epi_tile_screen<2>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
+                    case 3: epi_tile_screen<3>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
+                    default: epi_tile_screen<4>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                for (uint32_t h = half; h < half + nh; ++h) mbar_arrive_cluster(tempty_leader + 8 * h);   // 8 arrivals free a half
-                mbar_arrive(mempty0 + 8 * mbuf);                                                          // 4 arrivals free the meta buffer
+                for (uint32_t h = half; h < half + nh; ++h) mbar_arrive_cluster(tempty_leader + 8 * h);   // 16 arrivals free a half
+                mbar_arrive(mempty0 + 8 * mbuf);                                                          // 8 arrivals free the meta buffer
             }
             if (++mbuf == META_RING) { mbuf = 0; mphase ^= 1; }
             half = (half + nh) & 1u;
         }
-        if (q < nq) {
+        // the warps of the second column half hand their top-2 over (the tile-meta buffers are free by now)
+        Top2d *xch = reinterpret_cast<Top2d *>(&s_meta[0][0]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ch == 1) xch[row] = best;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ch == 0) {
+            const Top2d o = xch[row];
+            if (o.i1 >= 0) top2d_push(best, o.s1, o.i1);
+            if (o.i2 >= 0) top2d_push(best, o.s2, o.i2);
+        }
+        if (ch == 0 && q < nq) {
             // rows that were never candidates score exactly 0: a missing winner / runner-up is the lowest-index one of them
             if (best.i1 < 0) { best.i1 = 0; best.s1 = 0.0; }
             if (best.i2 < 0 && n_ann > 1) { best.i2 = (best.i1 == 0) ? 1 : 0; best.s2 = 0.0; }
