@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-DSKM_BUILDING", "-I", INCLUDE,
-]
+] + os.environ.get("SKM_EXTRA_NVCC", "").split()
 
 
 def _nvcc() -> str:

@@ -169,6 +169,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 constexpr uint32_t IDESC_WIDE = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(WIDE >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);
 constexpr uint32_t IDESC_NARROW = (2u << 4) | (0u << 7) | (0u << 10) | (uint32_t(NARROW >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);
 
+#ifdef SKM_TC_PROF
+__device__ long long g_tl[6][512];     // debug timeline of pair 0: see skm_debug_tc_timeline
+#define TL(k, t) do { if (blockIdx.x == 0 && (t) < 512) g_tl[k][t] = clock64(); } while (0)
+#else
+#define TL(k, t) do { } while (0)
+#endif
+
 struct Top2d {
     double s1, s2;
     int i1, i2;
@@ -177,6 +184,34 @@ struct Top2d {
 __device__ __forceinline__ void top2d_push(Top2d &t, double s, int i) {
     if (t.i1 < 0 || s > t.s1 || (s == t.s1 && i < t.i1)) { t.s2 = t.s1; t.i2 = t.i1; t.s1 = s; t.i1 = i; }
     else if (t.i2 < 0 || s > t.s2 || (s == t.s2 && i < t.i2)) { t.s2 = s; t.i2 = i; }
+}
+
+// Running top-2 of the screening epilogue.  Candidates are ordered by their float32 screening score whenever the two
+// scores differ by more than 1e-5 relative (the float32 error is < 4e-7, so the exact order is the same); only
+// near-ties are settled by the exact float64 scores, tie -> lower original index.  float64 arithmetic issued while the
+// tensor pipe is saturated costs thousands of cycles per candidate (measured: one candidate = 3900 cycles at K = 1024
+// against 600 with the tensor pipe idle), so the exact scores are otherwise formed once, after the last tile.
+struct Top2x {
+    float f1, f2;           // screening scores dot / ||m|| (float32)
+    int64_t d1, d2;         // exact dots
+    double im1, im2;        // 1 / ||m|| (float64) of the two rows
+    int i1, i2;             // original annotation indices, -1 = empty
+};
+__device__ __forceinline__ double exact_score(int64_t dot, double inv_qn, double inv_mn) { return double(dot) * (inv_qn * inv_mn); }
+// is the candidate (f, dot, im, i) ranked above the entry (fk, dk, imk, ik)?
+__device__ __forceinline__ bool ranks_above(float f, int64_t dot, double im, int i, float fk, int64_t dk, double imk, int ik, double inv_qn) {
+    if (f > fk * 1.00001f) return true;
+    if (f < fk * 0.99999f) return false;
+    const double s = exact_score(dot, inv_qn, im), sk = exact_score(dk, inv_qn, imk);
+    return s > sk || (s == sk && i < ik);
+}
+__device__ __forceinline__ void top2x_push(Top2x &t, float f, int64_t dot, double im, int i, double inv_qn) {
+    if (t.i1 < 0 || ranks_above(f, dot, im, i, t.f1, t.d1, t.im1, t.i1, inv_qn)) {
+        t.f2 = t.f1; t.d2 = t.d1; t.im2 = t.im1; t.i2 = t.i1;
+        t.f1 = f; t.d1 = dot; t.im1 = im; t.i1 = i;
+    } else if (t.i2 < 0 || ranks_above(f, dot, im, i, t.f2, t.d2, t.im2, t.i2, inv_qn)) {
+        t.f2 = f; t.d2 = dot; t.im2 = im; t.i2 = i;
+    }
 }
 
 // Per-tile epilogue operands ("tile meta"), precomputed per call by tile_meta_kernel in the layout the epilogue reads
@@ -220,7 +255,7 @@ __device__ __forceinline__ float plane_dot_f32(const uint32_t (&r)[NP][W], int i
 // tmem = this thread's TMEM lane address + first column of the tile; plane j starts `pstride` columns further.
 template <int NP>
 __device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride, int cbeg, int cend, const EpiTile &et, double inv_qn,
-                                                double qn, Top2d &best, float &thr) {
+                                                Top2x &best, float &thr) {
     constexpr int CW = (NP == 1) ? 32 : 16;       // columns per TMEM load
     constexpr int GW = (NP == 1) ? 8 : 4;         // columns per screening group
 #pragma unroll 1
@@ -257,10 +292,13 @@ __device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride,
             tmem_ld_wait();
             if ((gm >> g) & 1u) {
                 uint32_t pm = 0;                           // columns of the group that pass the float32 screen
+                float fe[GW];
 #pragma unroll
-                for (int e = 0; e < GW; ++e)
-                    if (plane_dot_f32<NP, GW>(v, e) * et.inv_m32[c0 + GW * g + e] >= thr) pm |= 1u << e;
-                while (pm) {                               // usually one: ONE copy of the exact path, operands picked by select chains
+                for (int e = 0; e < GW; ++e) {
+                    fe[e] = plane_dot_f32<NP, GW>(v, e) * et.inv_m32[c0 + GW * g + e];
+                    if (fe[e] >= thr) pm |= 1u << e;
+                }
+                while (pm) {                               // usually one: ONE copy of the insertion, operands picked by select chains
                     const int e = __ffs(pm) - 1;
                     pm &= pm - 1;
                     int64_t dot = 0;
@@ -271,12 +309,15 @@ __device__ __forceinline__ void epi_tile_screen(uint32_t tmem, uint32_t pstride,
                         for (int i = 1; i < GW; ++i) x = (e == i) ? v[j][i] : x;
                         dot = (dot << 8) + int64_t(int32_t(x));
                     }
+                    float f = fe[0];
+#pragma unroll
+                    for (int i = 1; i < GW; ++i) f = (e == i) ? fe[i] : f;
                     const int col = c0 + GW * g + e;
                     const int orig = et.orig[col];
-                    if (orig >= 0) top2d_push(best, double(dot) * (inv_qn * et.inv_mn[col]), orig);
+                    if (orig >= 0) top2x_push(best, f, dot, et.inv_mn[col], orig, inv_qn);
                 }
-                // below the runner-up by more than the float32 error of the screening product (3 * 2^-24)
-                if (best.i2 >= 0) thr = fmaxf(thr, __double2float_rd(best.s2 * qn) * 0.99999f);
+                // below the runner-up by more than the float32 error of the screening products
+                if (best.i2 >= 0) thr = fmaxf(thr, best.f2 * 0.99999f);
             }
         }
     }
@@ -432,6 +473,7 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     par_empty ^= 1u << h;
                 }
                 tc_fence_after();
+                if (lane == 0) TL(0, t);
                 const uint32_t idesc = td.width == WIDE ? IDESC_WIDE : IDESC_NARROW;
                 const uint32_t d0 = tmem_base + half * WIDE;
                 for (int kc = 0; kc < k_chunks; ++kc) {
@@ -468,6 +510,7 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 }
                 if (elect_one()) umma_commit_pair(tfull0 + 8 * half);       // accumulators of tile t complete (keyed by its first half)
                 __syncwarp();
+                if (lane == 0) TL(1, t);
                 half = (half + nh) & 1u;
             }
         }
@@ -479,11 +522,11 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int row = quarter * 32 + lane;
         const int64_t q = q0 + row;
         const double qn2 = (q < nq) ? qnorm2[q] : 0.0;
-        const double qn = sqrt(qn2);
-        const double inv_qn = qn2 > 0.0 ? 1.0 / qn : 0.0;
+        const double inv_qn = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
         const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
         const uint32_t tempty_leader = mapa_rank(tempty0, 0);
-        Top2d best{0.0, 0.0, -1, -1};
+        Top2d best{0.0, 0.0, -1, -1};                             // FULLOUT: every score is formed in float64 anyway
+        Top2x bx{0.f, 0.f, 0, 0, 0.0, 0.0, -1, -1};               // screening mode
         float thr = 1e-30f;                                       // > 0: zero dots are never candidates (see the final fill)
         volatile float *my_thr = &s_thr[ch][row], *other_thr = &s_thr[ch ^ 1][row];
         *my_thr = thr;
@@ -499,6 +542,8 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             mbar_wait(tfull0 + 8 * half, (par_full >> half) & 1u);
             par_full ^= 1u << half;
             tc_fence_after();
+            if (lane == 0 && warp == 2) TL(2, t);
+            if (lane == 0 && warp == 6) TL(4, t);
             const uint32_t tmem = lane_addr + half * WIDE;
             const uint32_t pstride = uint32_t(td.width);
             const int cbeg = ch * (td.width >> 1), cend = cbeg + (td.width >> 1);
@@ -514,14 +559,16 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 }
             } else {
                 switch (td.np) {
-                    case 1: epi_tile_screen<1>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
-                    case 2: epi_tile_screen<2>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
-                    case 3: epi_tile_screen<3>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
-                    default: epi_tile_screen<4>(tmem, pstride, cbeg, cend, tile, inv_qn, qn, best, thr); break;
+                    case 1: epi_tile_screen<1>(tmem, pstride, cbeg, cend, tile, inv_qn, bx, thr); break;
+                    case 2: epi_tile_screen<2>(tmem, pstride, cbeg, cend, tile, inv_qn, bx, thr); break;
+                    case 3: epi_tile_screen<3>(tmem, pstride, cbeg, cend, tile, inv_qn, bx, thr); break;
+                    default: epi_tile_screen<4>(tmem, pstride, cbeg, cend, tile, inv_qn, bx, thr); break;
                 }
             }
             tc_fence_before();
             __syncwarp();
+            if (lane == 0 && warp == 2) TL(3, t);
+            if (lane == 0 && warp == 6) TL(5, t);
             if (lane == 0) {
                 for (uint32_t h = half; h < half + nh; ++h) mbar_arrive_cluster(tempty_leader + 8 * h);   // 16 arrivals free a half
                 mbar_arrive(mempty0 + 8 * mbuf);                                                          // 8 arrivals free the meta buffer
@@ -530,6 +577,10 @@ apply_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             half = (half + nh) & 1u;
         }
         // the warps of the second column half hand their top-2 over (the tile-meta buffers are free by now)
+        if (!FULLOUT) {   // the exact scores of the two survivors, with the tensor pipe idle
+            best.i1 = bx.i1; best.s1 = bx.i1 >= 0 ? exact_score(bx.d1, inv_qn, bx.im1) : 0.0;
+            best.i2 = bx.i2; best.s2 = bx.i2 >= 0 ? exact_score(bx.d2, inv_qn, bx.im2) : 0.0;
+        }
         Top2d *xch = reinterpret_cast<Top2d *>(&s_meta[0][0]);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (ch == 1) xch[row] = best;
@@ -673,6 +724,13 @@ static size_t meta_bytes(int64_t rows) { return (tiles_offset(rows) + size_t(row
 }  // namespace skm
 
 extern "C" {
+
+#ifdef SKM_TC_PROF
+// debug builds only: timeline of CTA pair 0 (clock64 per tile): MMA tile start / issued, epilogue warp 2 and 6 start / end
+SKM_API int skm_debug_tc_timeline(long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, skm::tc::g_tl, sizeof(skm::tc::g_tl)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K) {
     using namespace skm::tc;
