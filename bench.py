@@ -396,13 +396,15 @@ def run_apply(ctx, args):
         e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
     total_ms, e2e_ms, k_ms = ctx.max_over_ranks([total_ms, e2e_ms, float(np.mean(kern_ms))])
     ms = total_ms / args.steps
-    ops = 2.0 * batch.n * n_ann * 1024 * prep.n_planes             # int8 MACs x 2 actually issued (K padded to 1024)
+    ops = 2.0 * batch.n * prep.issued_macs_per_query()              # int8 MACs x 2 actually issued (per tile: width x planes x padded K)
+    tiles = prep.tiles()
     peak, src = tensor_peak_int8()
     line = {"metric": "sequences/sec apply", "value": ctx.world * args.nseq / (ms * 1e-3), "unit": "sequences/s", "n_gpus": ctx.world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8 x int8 -> int32 (exact), float64 scaling", "data": "synthetic",
             "config": {"workload": f"dense apply: {args.nseq} queries/GPU (mean len 350) vs {n_ann} annotations, miqs k=3 (K=1000), "
-                                   f"{prep.n_planes} base-256 digit planes; counts + norms + tcgen05 GEMM + top-2",
+                                   f"{len(tiles)} annotation tiles, {float(tiles[:, 2].mean()):.2f} base-256 digit planes per tile (max {prep.n_planes}); "
+                                   f"counts + norms + tcgen05 GEMM + top-2",
                        "l2": "query counts 4 GB larger than L2", "parallelism": f"query-sharded x{ctx.world}, matrix replicated, no collective"},
             "clocks": clocks, "gpu_launches": 4 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "apply_tc_kernel", "achieved": ops / (k_ms * 1e-3) / 1e12, "peak": peak,

@@ -20,10 +20,8 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 Q = torch.randint(0, 4, (a.nq, a.K), generator=g, device=dev, dtype=torch.int32)
 M = torch.randint(0, a.mmax + 1, (a.ann, a.K), generator=g, device=dev, dtype=torch.int64)
 prep = E.prepare_annotations(M)
-hdr = prep.planes[:8].view(torch.int32).cpu().numpy()          # blob header: n_tiles, rows per plane
-n_tiles, rows = int(hdr[0]), int(hdr[1])
-toff = 1024 + rows * 4                                         # TileDesc {row0, width, np, pad} after the permutation
-tiles = prep.planes[toff:toff + 16 * n_tiles].view(torch.int32).cpu().numpy().reshape(-1, 4)
+tiles = prep.tiles()
+n_tiles = len(tiles)
 qn2 = E.row_norm2(Q)
 for _ in range(2):
     r = E.apply_tc(Q, prep, qn2)
@@ -35,6 +33,6 @@ for _ in range(a.reps):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 Kp = (a.K + 127) // 128 * 128
-ops = 2.0 * a.nq * float((tiles[:, 1] * tiles[:, 2]).sum()) * Kp
+ops = 2.0 * a.nq * prep.issued_macs_per_query()
 print(f"nq={a.nq} ann={a.ann} K={a.K} mmax={a.mmax} planes(max)={prep.n_planes} tiles={n_tiles} mean planes/tile={tiles[:, 2].mean():.2f} "
       f"ms={ms:.3f} TOP/s={ops / ms / 1e9:.1f}")

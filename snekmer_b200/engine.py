@@ -491,6 +491,19 @@ class PreparedAnnotations:
     K: int
     mnorm2: torch.Tensor        # float64 [A]
 
+    def tiles(self) -> np.ndarray:
+        """The annotation tiles of the prepared matrix as int32 [n_tiles, 3] = (first sorted row, width, digit planes)
+        (blob header: n_tiles, rows per plane; TileDesc records follow the row permutation)."""
+        hdr = self.planes[:8].view(torch.int32).cpu().numpy()
+        n_tiles, rows = int(hdr[0]), int(hdr[1])
+        off = 1024 + rows * 4
+        return self.planes[off:off + 16 * n_tiles].view(torch.int32).cpu().numpy().reshape(-1, 4)[:, :3].copy()
+
+    def issued_macs_per_query(self) -> int:
+        """int8 multiply-accumulates apply_tc issues per query row: sum over tiles of width x planes x padded K."""
+        t = self.tiles()
+        return int((t[:, 1].astype(np.int64) * t[:, 2]).sum()) * ((self.K + 127) // 128 * 128)
+
 
 def prepare_annotations(M: torch.Tensor, mnorm2: Optional[torch.Tensor] = None) -> Optional[PreparedAnnotations]:
     """Digit planes of M for apply_tc, or None when M is outside the tensor-core envelope
