@@ -177,22 +177,27 @@ SKM_API int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, i
                   void *workspace, size_t workspace_bytes, skm_stream_t stream);
 
 /* Annotation-major COO (key = ann * S + code) -> k-mer-major CSC for the SpMM:
- * d_colptr int64 [S+1], d_rows int32 [nnz] (annotation), d_w float [nnz] =
- * M[a, c] / ||m_a|| (sklearn normalize, apply.smk:282), d_mnorm2 (nullable) = ||m_a||^2. */
+ * d_colptr int64 [S+1], d_rows int32 [nnz] (annotation), d_mvals int32 [nnz] = M[a, c],
+ * d_mnorm2 (nullable) = ||m_a||^2 (exact integer sum, as float64), d_inv_m32 (nullable) =
+ * float32 1 / ||m_a|| (0 for empty rows), *d_max_m = largest entry (callers must check it
+ * is < 2^31: larger entries do not fit d_mvals). */
 SKM_API size_t skm_csc_build_workspace(int64_t nnz, int64_t n_ann);
 SKM_API int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, int64_t S,
-                  int64_t n_ann, int64_t *d_colptr, int32_t *d_rows, float *d_w,
-                  double *d_mnorm2, void *workspace, size_t workspace_bytes,
-                  skm_stream_t stream);
+                  int64_t n_ann, int64_t *d_colptr, int32_t *d_rows, int32_t *d_mvals,
+                  double *d_mnorm2, float *d_inv_m32, int64_t *d_max_m, void *workspace,
+                  size_t workspace_bytes, skm_stream_t stream);
 
 /* (a16/a17 at large K) apply as SpMM: queries are CSR rows over CODES (skm_count_csr with
- * d_col_of_code = NULL, so that ||q|| runs over all valid k-mers, apply.smk:268-276);
- * scores are accumulated in float32 (|rel. error| ~ 1e-7, tolerance of the path 1e-5).
- * n_ann <= 51200 per call: shard the annotations and merge with skm_top2_merge.
- * d_qnorm2 (nullable) receives ||q||^2. */
+ * d_col_of_code = NULL, so that ||q|| runs over all valid k-mers, apply.smk:268-276).
+ * Dots are accumulated EXACTLY in integer shared-memory accumulators (acc_bits = 32 when
+ * max(M) * (largest row total of the queries) < 2^32, else 64); scores are
+ * dot * (1/||q||) * (1/||m||) in float64 like skm_apply_dense, ties -> lowest index.
+ * n_ann <= 51200 (32-bit) or 25600 (64-bit) per call: shard the annotations and merge with
+ * skm_top2_merge.  d_qnorm2 (nullable) receives ||q||^2. */
 SKM_API int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int32_t *d_vals,
                      int64_t nq, const int64_t *d_colptr, const int32_t *d_rows,
-                     const float *d_w, int64_t n_ann, int32_t *d_top1, int32_t *d_top2,
+                     const int32_t *d_mvals, const double *d_mnorm2, const float *d_inv_m32,
+                     int64_t n_ann, int acc_bits, int32_t *d_top1, int32_t *d_top2,
                      double *d_score1, double *d_score2, double *d_qnorm2,
                      skm_stream_t stream);
 

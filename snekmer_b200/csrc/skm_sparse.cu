@@ -10,12 +10,14 @@
 //  skm_coo_merge      sum of COO lists with equal keys (sort by key + reduce by key):
 //                     Merge.merge_dataframes (learn.smk:467-494) for sparse matrices, and the
 //                     fan-in after an all-gather of per-GPU lists.
-//  skm_csc_build      annotation-major COO -> k-mer-major CSC with cosine weights
-//                     w = M[a, c] / ||m_a||  (float32) for the SpMM.
-//  skm_apply_sparse   kernel (d) as SpMM: per query (CSR row of k-mer codes + counts) the
-//                     weighted columns of the CSC are accumulated in a shared-memory score
-//                     vector (one warp per query, lanes own distinct annotations: no atomics),
-//                     followed by the top-2 scan (apply.smk:278-335).
+//  skm_csc_build      annotation-major COO -> k-mer-major CSC (annotation index + int32 count per
+//                     entry), exact ||m_a||^2 and float32 1 / ||m_a|| for the screening pass.
+//  skm_apply_sparse   kernel (d) as SpMM with EXACT integer dots: one CTA per query keeps one
+//                     integer accumulator per annotation in shared memory (up to 51,200), its
+//                     warps walk the CSC columns of the query's k-mers and add count x M[a, c]
+//                     with shared-memory integer atomics (order-independent, hence reproducible),
+//                     then scan the accumulators for the top-2 (float32 screening, exact float64
+//                     scores for the survivors; apply.smk:278-335).
 //  window_keys_kernel is also the key generator of skm_count_csr (skm_count.cu).
 #include <cub/cub.cuh>
 
@@ -29,14 +31,15 @@ constexpr int SP_SYM_BYTES = ts_sym_bytes(SP_SEG);
 
 // keys[p] for every residue position p of [off[0], off[nseq]) (p = position of the window's LAST residue):
 //   MODE 0: column (col_of_code) or code, 32-bit, all-ones when invalid / filtered
-//   MODE 1: ann_id[row] * S + code, 64-bit, all-ones when invalid or the sequence is not annotated
+//   MODE 1: ann_id[row] * S + code, 64-bit, `invalid` (= n_ann * S, one past the largest key) when the window is
+//           invalid or the sequence is not annotated: the sort then only needs the bits of n_ann * S
 template <int MODE, typename KeyT>
 __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *__restrict__ res, int64_t nres,
                                                                  const int64_t *__restrict__ off, int64_t nseq,
                                                                  const uint8_t *__restrict__ lut, uint32_t nsym, int k,
                                                                  uint32_t pow_k1, const int32_t *__restrict__ col_of_code,
                                                                  const int32_t *__restrict__ ann_id, uint64_t S,
-                                                                 KeyT *__restrict__ keys) {
+                                                                 KeyT invalid, KeyT *__restrict__ keys) {
     extern __shared__ __align__(128) uint8_t s_sym[];
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_ctl[4];
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *
     uint64_t ann_base = ~0ull;
     ts_range_scan_rows<uint32_t>(res, nres, off, nseq, s_lut, s_sym, SP_SEG, k, nsym, pow_k1, /*origin=*/0, s_ctl,
                                  [&](int64_t rel_end, int64_t row, uint32_t code, bool ok) {
-                                     KeyT key = KeyT(~KeyT(0));
+                                     KeyT key = invalid;
                                      if (ok) {
                                          if (MODE == 0) {
                                              if (col_of_code) { const int32_t c = __ldg(col_of_code + code); if (c >= 0) key = KeyT(c); }
@@ -64,9 +67,12 @@ __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *
                                  });
 }
 
-__global__ void coo_finish_kernel(const uint64_t *__restrict__ uniq, const int64_t *__restrict__ num_runs, int64_t *__restrict__ nnz) {
-    const int64_t n = *num_runs;
-    *nnz = (n > 0 && uniq[n - 1] == ~0ull) ? n - 1 : n;
+// the runs of the invalid key (and of the all-ones fill outside the sequences) sort last: drop them
+__global__ void coo_finish_kernel(const uint64_t *__restrict__ uniq, const int64_t *__restrict__ num_runs, uint64_t invalid,
+                                  int64_t *__restrict__ nnz) {
+    int64_t n = *num_runs;
+    while (n > 0 && uniq[n - 1] >= invalid) --n;
+    *nnz = n;
 }
 
 // ---- CSC build -------------------------------------------------------------------------------
@@ -78,9 +84,6 @@ __global__ void __launch_bounds__(256) coo_row_norm2_kernel(const uint64_t *__re
         atomicAdd(norm2 + keys[i] / S, v * v);
     }
 }
-__global__ void norm2_to_double_kernel(const unsigned long long *__restrict__ in, int64_t n, double *__restrict__ out) {
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) out[i] = double(in[i]);
-}
 __global__ void __launch_bounds__(256) csc_keys_kernel(const uint64_t *__restrict__ keys, int64_t nnz, uint64_t S,
                                                        uint64_t n_ann, uint64_t *__restrict__ out, int64_t *__restrict__ perm) {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x) {
@@ -90,73 +93,196 @@ __global__ void __launch_bounds__(256) csc_keys_kernel(const uint64_t *__restric
     }
 }
 __global__ void __launch_bounds__(256) csc_emit_kernel(const uint64_t *__restrict__ skeys, const int64_t *__restrict__ perm,
-                                                       const int64_t *__restrict__ vals, const unsigned long long *__restrict__ norm2,
-                                                       int64_t nnz, uint64_t n_ann, int32_t *__restrict__ rows,
-                                                       float *__restrict__ w, unsigned long long *__restrict__ colcount) {
+                                                       const int64_t *__restrict__ vals, int64_t nnz, uint64_t n_ann,
+                                                       int32_t *__restrict__ rows, int32_t *__restrict__ mvals,
+                                                       unsigned long long *__restrict__ colcount, unsigned long long *__restrict__ max_m) {
+    unsigned long long mx = 0;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x) {
         const uint64_t c = skeys[i] / n_ann, a = skeys[i] - c * n_ann;
         rows[i] = int32_t(a);
-        const double n2 = double(norm2[a]);
-        w[i] = n2 > 0.0 ? float(double(vals[perm[i]]) / sqrt(n2)) : 0.0f;
+        const unsigned long long v = (unsigned long long)vals[perm[i]];
+        mvals[i] = int32_t(v);                 // callers check *max_m < 2^31
+        mx = v > mx ? v : mx;
         atomicAdd(colcount + c + 1, 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(FULL, mx, o); mx = x > mx ? x : mx; }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_m, mx);
+}
+__global__ void norm2_finish_kernel(const unsigned long long *__restrict__ in, int64_t n, double *__restrict__ norm2, float *__restrict__ inv32) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const double m2 = double(in[i]);
+        if (norm2) norm2[i] = m2;
+        if (inv32) inv32[i] = m2 > 0.0 ? float(1.0 / sqrt(m2)) : 0.0f;
     }
 }
 
 // ---- SpMM + top-2 ------------------------------------------------------------------------------
-struct Top2f {
-    float s1, s2;
+struct Top2d {
+    double s1, s2;
     int i1, i2;
 };
-__device__ __forceinline__ bool better_f(float s, int i, float t, int j) { return s > t || (s == t && i < j); }
-__device__ __forceinline__ void top2f_push(Top2f &t, float s, int i) {
+// higher score first; equal scores -> lower annotation index (np.argsort(-S) on exact ties)
+__device__ __forceinline__ void top2d_push(Top2d &t, double s, int i) {
     if (i < 0) return;
-    if (t.i1 < 0 || better_f(s, i, t.s1, t.i1)) { t.s2 = t.s1; t.i2 = t.i1; t.s1 = s; t.i1 = i; }
-    else if (t.i2 < 0 || better_f(s, i, t.s2, t.i2)) { t.s2 = s; t.i2 = i; }
+    if (t.i1 < 0 || s > t.s1 || (s == t.s1 && i < t.i1)) { t.s2 = t.s1; t.i2 = t.i1; t.s1 = s; t.i1 = i; }
+    else if (t.i2 < 0 || s > t.s2 || (s == t.s2 && i < t.i2)) { t.s2 = s; t.i2 = i; }
+}
+// Per-thread running top-2 of the accumulator scan, ordered by the float32 screening score dot / ||m|| whenever two
+// scores differ by more than 1e-5 relative (their float32 error is < 4e-7); near-ties are settled by the exact
+// float64 scores, tie -> lower index.  The same scheme as the tensor-core kernel (skm_apply_tc.cu).
+struct Top2x {
+    float f1, f2;
+    unsigned long long d1, d2;      // exact dots
+    int i1, i2;
+};
+__device__ __forceinline__ double sp_exact(unsigned long long dot, double inv_qn, const double *__restrict__ mnorm2, int a) {
+    return double(dot) * (inv_qn * (1.0 / sqrt(mnorm2[a])));
+}
+__device__ __forceinline__ bool sp_above(float f, unsigned long long dot, int i, float fk, unsigned long long dk, int ik, double inv_qn,
+                                         const double *__restrict__ mnorm2) {
+    if (f > fk * 1.00001f) return true;
+    if (f < fk * 0.99999f) return false;
+    const double s = sp_exact(dot, inv_qn, mnorm2, i), sk = sp_exact(dk, inv_qn, mnorm2, ik);
+    return s > sk || (s == sk && i < ik);
+}
+__device__ __forceinline__ void top2x_push(Top2x &t, float f, unsigned long long dot, int i, double inv_qn, const double *__restrict__ mnorm2) {
+    if (t.i1 < 0 || sp_above(f, dot, i, t.f1, t.d1, t.i1, inv_qn, mnorm2)) {
+        t.f2 = t.f1; t.d2 = t.d1; t.i2 = t.i1;
+        t.f1 = f; t.d1 = dot; t.i1 = i;
+    } else if (t.i2 < 0 || sp_above(f, dot, i, t.f2, t.d2, t.i2, inv_qn, mnorm2)) {
+        t.f2 = f; t.d2 = dot; t.i2 = i;
+    }
 }
 
-// one warp per query; acc = n_ann floats of shared memory per warp
-__global__ void __launch_bounds__(256) apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ qcols,
-                                                           const int32_t *__restrict__ qvals, int64_t nq,
-                                                           const int64_t *__restrict__ colptr, const int32_t *__restrict__ rows,
-                                                           const float *__restrict__ w, int n_ann,
-                                                           int32_t *__restrict__ top1, int32_t *__restrict__ top2,
-                                                           double *__restrict__ sc1, double *__restrict__ sc2,
-                                                           double *__restrict__ qnorm2_out) {
-    extern __shared__ float s_acc[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    float *acc = s_acc + size_t(wid) * n_ann;
-    for (int a = lane; a < n_ann; a += 32) acc[a] = 0.0f;
-    __syncwarp();
-    for (int64_t q = int64_t(blockIdx.x) * nw + wid; q < nq; q += int64_t(gridDim.x) * nw) {
+constexpr int SPA_THREADS = 512;
+constexpr int SPA_EB = 512;        // query entries staged per block
+constexpr int SPA_SEG = 256;       // CSC entries per segment (8 per lane)
+
+// One CTA per query (grid-stride).  acc: one integer per annotation in shared memory (AccT = uint32 when every dot
+// fits 32 bits — the host checks max(M) * max row total < 2^32 — else uint64).
+//   walk   the query's (k-mer, count) entries are staged in shared memory with their column ranges; the warps share
+//          the columns segment by segment: acc[row] += count * M[row, code].
+//   scan   every thread owns the same accumulators for every query (4 adjacent ones per step): float32 screening
+//          score acc * inv_m32 against the thread's running runner-up, survivors inserted into a Top2x; the
+//          accumulators are zeroed on the way.  The threads' top-2 lists are then merged with exact float64 scores.
+template <typename AccT>
+__global__ void __launch_bounds__(SPA_THREADS, 1)
+apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ qcols, const int32_t *__restrict__ qvals,
+                    int64_t nq, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rows,
+                    const int32_t *__restrict__ mvals, const double *__restrict__ mnorm2, const float *__restrict__ inv_m32,
+                    int n_ann, int32_t *__restrict__ top1, int32_t *__restrict__ top2, double *__restrict__ sc1,
+                    double *__restrict__ sc2, double *__restrict__ qnorm2_out) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ unsigned long long s_n2;
+    __shared__ Top2d s_top[SPA_THREADS / 32];
+    __shared__ int64_t s_p0[SPA_EB];
+    __shared__ int s_len[SPA_EB];
+    __shared__ uint32_t s_cnt[SPA_EB];
+    AccT *acc = reinterpret_cast<AccT *>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = SPA_THREADS / 32;
+    constexpr int PER = 16 / sizeof(AccT);                 // accumulators per 16-byte step of the scan
+    const int n_pad = (n_ann + PER - 1) / PER * PER;
+    for (int i = tid; i < n_pad; i += SPA_THREADS) acc[i] = 0;
+    if (tid == 0) s_n2 = 0;
+    __syncthreads();
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
         const int64_t e0 = __ldg(rowptr + q), e1 = __ldg(rowptr + q + 1);
-        double n2 = 0.0;
-        for (int64_t e = e0; e < e1; ++e) {
-            const uint32_t c = __ldg(qcols + e);
-            const float cnt = float(__ldg(qvals + e));
-            n2 += double(cnt) * double(cnt);
-            const int64_t p0 = __ldg(colptr + c), p1 = __ldg(colptr + c + 1);
-            for (int64_t p = p0 + lane; p < p1; p += 32) acc[__ldg(rows + p)] += cnt * __ldg(w + p);   // distinct annotations per column
-            __syncwarp();
-        }
-        const float inv = n2 > 0.0 ? float(1.0 / sqrt(n2)) : 0.0f;
-        Top2f t{0.f, 0.f, -1, -1};
-        for (int a = lane; a < n_ann; a += 32) {
-            top2f_push(t, acc[a] * inv, a);
-            acc[a] = 0.0f;
+        // ---- walk: blocks of SPA_EB query entries are staged in shared memory; every column is cut into segments of
+        // SPA_SEG entries and segment s of entry j goes to warp (j + s) mod NW, so that long columns (popular k-mers
+        // meet thousands of annotations) spread over the CTA.  A lane loads its SPA_SEG / 32 entries of the segment
+        // before the first atomic: the loads of a segment are all in flight together. ----
+        unsigned long long n2 = 0;
+        for (int64_t b0 = e0; b0 < e1; b0 += SPA_EB) {
+            const int nb = (e1 - b0 < SPA_EB) ? int(e1 - b0) : SPA_EB;
+            for (int j = tid; j < nb; j += SPA_THREADS) {
+                const uint32_t c = __ldg(qcols + b0 + j);
+                const uint32_t cnt = uint32_t(__ldg(qvals + b0 + j));
+                const int64_t p0 = __ldg(colptr + c);
+                s_p0[j] = p0;
+                s_len[j] = int(__ldg(colptr + c + 1) - p0);
+                s_cnt[j] = cnt;
+                n2 += (unsigned long long)cnt * cnt;
+            }
+            __syncthreads();
+            for (int j = 0; j < nb; ++j) {
+                const int len = s_len[j];
+                int seg = (warp - j) & (NW - 1);
+                if (seg * SPA_SEG >= len) continue;
+                const AccT cnt = AccT(s_cnt[j]);
+                const int64_t p0 = s_p0[j];
+                for (; seg * SPA_SEG < len; seg += NW) {
+                    const int64_t pb = p0 + int64_t(seg) * SPA_SEG;
+                    const int n = min(SPA_SEG, len - seg * SPA_SEG);
+                    int r[SPA_SEG / 32];
+                    uint32_t m[SPA_SEG / 32];
+#pragma unroll
+                    for (int u = 0; u < SPA_SEG / 32; ++u) {
+                        const int idx = lane + 32 * u;
+                        r[u] = -1;
+                        m[u] = 0;
+                        if (idx < n) { r[u] = __ldg(rows + pb + idx); m[u] = uint32_t(__ldg(mvals + pb + idx)); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < SPA_SEG / 32; ++u)
+                        if (r[u] >= 0) atomicAdd(&acc[r[u]], cnt * AccT(m[u]));
+                }
+            }
+            __syncthreads();
         }
 #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+        if (lane == 0 && n2) atomicAdd(&s_n2, n2);
+        __syncthreads();
+        // ---- scan ----
+        const double qn2 = double(s_n2);
+        const double inv_qn = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
+        Top2x bx{0.f, 0.f, 0ull, 0ull, -1, -1};
+        float thr = 1e-30f;                                    // > 0: zero dots are never candidates (see the final fill)
+        for (int a0 = tid * PER; a0 < n_pad; a0 += SPA_THREADS * PER) {
+            AccT v[PER];
+            *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(&acc[a0]);
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) any |= (v[i] != 0);
+            if (any) {
+                *reinterpret_cast<uint4 *>(&acc[a0]) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    if (v[i] != 0) {
+                        const float f = float(v[i]) * __ldg(inv_m32 + a0 + i);
+                        if (f >= thr) {
+                            top2x_push(bx, f, (unsigned long long)v[i], a0 + i, inv_qn, mnorm2);
+                            if (bx.i2 >= 0) thr = fmaxf(thr, bx.f2 * 0.99999f);
+                        }
+                    }
+                }
+            }
+        }
+        Top2d best{0.0, 0.0, -1, -1};
+        if (bx.i1 >= 0) { best.i1 = bx.i1; best.s1 = sp_exact(bx.d1, inv_qn, mnorm2, bx.i1); }
+        if (bx.i2 >= 0) { best.i2 = bx.i2; best.s2 = sp_exact(bx.d2, inv_qn, mnorm2, bx.i2); }
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float os1 = __shfl_xor_sync(FULL, t.s1, o), os2 = __shfl_xor_sync(FULL, t.s2, o);
-            const int oi1 = __shfl_xor_sync(FULL, t.i1, o), oi2 = __shfl_xor_sync(FULL, t.i2, o);
-            top2f_push(t, os1, oi1);
-            top2f_push(t, os2, oi2);
+            const double os1 = __shfl_xor_sync(FULL, best.s1, o), os2 = __shfl_xor_sync(FULL, best.s2, o);
+            const int oi1 = __shfl_xor_sync(FULL, best.i1, o), oi2 = __shfl_xor_sync(FULL, best.i2, o);
+            top2d_push(best, os1, oi1);
+            top2d_push(best, os2, oi2);
         }
-        if (lane == 0) {
-            top1[q] = t.i1; sc1[q] = (t.i1 >= 0) ? double(t.s1) : 0.0;
-            top2[q] = t.i2; sc2[q] = (t.i2 >= 0) ? double(t.s2) : nan("");
-            if (qnorm2_out) qnorm2_out[q] = n2;
+        if (lane == 0) s_top[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NW; ++w) { top2d_push(best, s_top[w].s1, s_top[w].i1); top2d_push(best, s_top[w].s2, s_top[w].i2); }
+            // annotations that were never candidates score exactly 0: a missing winner / runner-up is the lowest-index one of them
+            if (best.i1 < 0) { best.i1 = 0; best.s1 = 0.0; }
+            if (best.i2 < 0 && n_ann > 1) { best.i2 = (best.i1 == 0) ? 1 : 0; best.s2 = 0.0; }
+            top1[q] = best.i1; sc1[q] = best.s1;
+            top2[q] = best.i2; sc2[q] = best.i2 >= 0 ? best.s2 : nan("");
+            if (qnorm2_out) qnorm2_out[q] = qn2;
+            s_n2 = 0;
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -178,7 +304,7 @@ int skm_window_keys_u32(const uint8_t *d_residues, int64_t nres, const int64_t *
     const int64_t max_grid = (nres + SP_SEG - 1) / SP_SEG;
     if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
     window_keys_kernel<0, uint32_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
-                                                                                      pow_k1, d_col_of_code, nullptr, 0, d_keys);
+                                                                                      pow_k1, d_col_of_code, nullptr, 0, 0xFFFFFFFFu, d_keys);
     SKM_LAUNCH_CHECK("window_keys_kernel<0>");
     return SKM_OK;
 }
@@ -219,6 +345,7 @@ int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int64_t *d_o
     void *temp = p + 2 * seg;
     size_t temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
     const uint64_t S = (uint64_t)S128;
+    const uint64_t invalid = uint64_t(n_ann) * S;
     uint32_t pow_k1 = 1;
     for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
     int64_t grid = int64_t(sm_count()) * 8;
@@ -227,16 +354,15 @@ int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int64_t *d_o
     // positions outside [off[0], off[nseq]) are not written by the kernel
     SKM_CUDA_TRY(cudaMemsetAsync(keys_a, 0xFF, size_t(nres) * 8, st));
     window_keys_kernel<1, uint64_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
-                                                                                      pow_k1, nullptr, d_ann_id, S, keys_a);
+                                                                                      pow_k1, nullptr, d_ann_id, S, invalid, keys_a);
     SKM_LAUNCH_CHECK("window_keys_kernel<1>");
-    // all-ones (invalid) sorts last because every bit up to 63 takes part: sort on [0, 64) only when needed
-    const int end_bit = 64;
-    (void)bits_for;
+    // keys are < 2^end_bit except the all-ones fill, whose low bits are all ones too: it still sorts last
+    const int end_bit = bits_for((unsigned __int128)invalid + 1);
     SKM_CUDA_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, nres, 0, end_bit, st));
     int64_t *num_runs = reinterpret_cast<int64_t *>(keys_a);     // keys_a is free after the sort
     temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
     SKM_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, keys_b, d_keys_out, d_vals_out, num_runs, (int)nres, st));
-    coo_finish_kernel<<<1, 1, 0, st>>>(d_keys_out, num_runs, d_nnz);
+    coo_finish_kernel<<<1, 1, 0, st>>>(d_keys_out, num_runs, invalid, d_nnz);
     SKM_LAUNCH_CHECK("coo_finish_kernel");
     return SKM_OK;
 }
@@ -286,15 +412,17 @@ size_t skm_csc_build_workspace(int64_t nnz, int64_t n_ann) {
 }
 
 int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, int64_t S, int64_t n_ann,
-                  int64_t *d_colptr, int32_t *d_rows, float *d_w, double *d_mnorm2, void *workspace,
-                  size_t workspace_bytes, skm_stream_t stream) {
+                  int64_t *d_colptr, int32_t *d_rows, int32_t *d_mvals, double *d_mnorm2, float *d_inv_m32,
+                  int64_t *d_max_m, void *workspace, size_t workspace_bytes, skm_stream_t stream) {
     using namespace skm;
     if (nnz < 0 || S <= 0 || S > SKM_DENSE_MAX_SPACE || n_ann < 0 || !d_colptr) { set_error("skm_csc_build: bad arguments"); return SKM_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     SKM_CUDA_TRY(cudaMemsetAsync(d_colptr, 0, size_t(S + 1) * 8, st));
     if (d_mnorm2 && n_ann > 0) SKM_CUDA_TRY(cudaMemsetAsync(d_mnorm2, 0, size_t(n_ann) * 8, st));
+    if (d_inv_m32 && n_ann > 0) SKM_CUDA_TRY(cudaMemsetAsync(d_inv_m32, 0, size_t(n_ann) * 4, st));
+    if (d_max_m) SKM_CUDA_TRY(cudaMemsetAsync(d_max_m, 0, 8, st));
     if (nnz == 0) return SKM_OK;
-    if (!d_keys || !d_vals || !d_rows || !d_w) { set_error("skm_csc_build: NULL argument"); return SKM_ERR_INVALID; }
+    if (!d_keys || !d_vals || !d_rows || !d_mvals || !d_max_m) { set_error("skm_csc_build: NULL argument"); return SKM_ERR_INVALID; }
     const size_t need = skm_csc_build_workspace(nnz, n_ann);
     if (!workspace || workspace_bytes < need) { set_error("skm_csc_build: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
     char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
@@ -310,40 +438,42 @@ int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, in
     SKM_LAUNCH_CHECK("coo_row_norm2_kernel");
     csc_keys_kernel<<<grid, 256, 0, st>>>(d_keys, nnz, (uint64_t)S, (uint64_t)n_ann, k_in, perm_in);
     SKM_LAUNCH_CHECK("csc_keys_kernel");
-    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, perm_in, perm_out, nnz, 0, 64, st));
-    csc_emit_kernel<<<grid, 256, 0, st>>>(k_out, perm_out, d_vals, norm2, nnz, (uint64_t)n_ann, d_rows, d_w,
-                                          reinterpret_cast<unsigned long long *>(d_colptr));
+    const int end_bit = bits_for((unsigned __int128)S * (unsigned __int128)std::max<int64_t>(n_ann, 1));
+    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k_in, k_out, perm_in, perm_out, nnz, 0, end_bit, st));
+    csc_emit_kernel<<<grid, 256, 0, st>>>(k_out, perm_out, d_vals, nnz, (uint64_t)n_ann, d_rows, d_mvals,
+                                          reinterpret_cast<unsigned long long *>(d_colptr), reinterpret_cast<unsigned long long *>(d_max_m));
     SKM_LAUNCH_CHECK("csc_emit_kernel");
     temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
     SKM_CUDA_TRY(cub::DeviceScan::InclusiveSum(temp, temp_bytes, d_colptr, d_colptr, S + 1, st));
-    if (d_mnorm2 && n_ann > 0) {
-        norm2_to_double_kernel<<<(int)std::min<int64_t>((n_ann + 255) / 256, 1024), 256, 0, st>>>(norm2, n_ann, d_mnorm2);
-        SKM_LAUNCH_CHECK("norm2_to_double_kernel");
+    if ((d_mnorm2 || d_inv_m32) && n_ann > 0) {
+        norm2_finish_kernel<<<(int)std::min<int64_t>((n_ann + 255) / 256, 1024), 256, 0, st>>>(norm2, n_ann, d_mnorm2, d_inv_m32);
+        SKM_LAUNCH_CHECK("norm2_finish_kernel");
     }
     return SKM_OK;
 }
 
 int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int32_t *d_vals, int64_t nq,
-                     const int64_t *d_colptr, const int32_t *d_rows, const float *d_w, int64_t n_ann,
-                     int32_t *d_top1, int32_t *d_top2, double *d_score1, double *d_score2, double *d_qnorm2,
-                     skm_stream_t stream) {
+                     const int64_t *d_colptr, const int32_t *d_rows, const int32_t *d_mvals, const double *d_mnorm2,
+                     const float *d_inv_m32, int64_t n_ann, int acc_bits, int32_t *d_top1, int32_t *d_top2,
+                     double *d_score1, double *d_score2, double *d_qnorm2, skm_stream_t stream) {
     using namespace skm;
-    if (nq < 0 || n_ann < 0 || n_ann > 50 * 1024) { set_error("skm_apply_sparse: n_ann=%lld outside [0, 51200] (shard the annotations)", (long long)n_ann); return n_ann > 50 * 1024 ? SKM_ERR_UNSUPPORTED : SKM_ERR_INVALID; }
+    if (acc_bits != 32 && acc_bits != 64) { set_error("skm_apply_sparse: acc_bits must be 32 or 64"); return SKM_ERR_INVALID; }
+    const int64_t cap = (200 * 1024) / (acc_bits / 8);
+    if (nq < 0 || n_ann <= 0 || n_ann > cap) { set_error("skm_apply_sparse: n_ann=%lld outside [1, %lld] for %d-bit accumulators (shard the annotations)", (long long)n_ann, (long long)cap, acc_bits); return n_ann > cap ? SKM_ERR_UNSUPPORTED : SKM_ERR_INVALID; }
     if (nq == 0) return SKM_OK;
-    if (!d_rowptr || !d_colptr || !d_top1 || !d_top2 || !d_score1 || !d_score2) { set_error("skm_apply_sparse: NULL argument"); return SKM_ERR_INVALID; }
-    // warps per CTA: as many score vectors as fit ~200 KB, at most 8
-    const size_t per_warp = size_t(std::max<int64_t>(n_ann, 1)) * 4;
-    int nw = int((200 * 1024) / per_warp);
-    if (nw > 8) nw = 8;
-    if (nw < 1) nw = 1;
-    const size_t smem = per_warp * nw;
-    int per_sm = int((227 * 1024) / (smem + 1024));
-    if (per_sm > 2048 / (32 * nw)) per_sm = 2048 / (32 * nw);
-    if (per_sm < 1) per_sm = 1;
-    const int grid = (int)std::min<int64_t>((nq + nw - 1) / nw, int64_t(sm_count()) * per_sm);
-    SKM_CUDA_TRY(cudaFuncSetAttribute(apply_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    apply_sparse_kernel<<<grid, 32 * nw, smem, (cudaStream_t)stream>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_w, (int)n_ann, d_top1,
-                                                                       d_top2, d_score1, d_score2, d_qnorm2);
+    if (!d_rowptr || !d_colptr || !d_mnorm2 || !d_inv_m32 || !d_top1 || !d_top2 || !d_score1 || !d_score2) { set_error("skm_apply_sparse: NULL argument"); return SKM_ERR_INVALID; }
+    const size_t smem = std::max<size_t>(size_t(n_ann + 4) * (acc_bits / 8), 116 * 1024);   // > half an SM: one CTA per SM by construction
+    const int grid = (int)std::min<int64_t>(nq, int64_t(sm_count()));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (acc_bits == 32) {
+        SKM_CUDA_TRY(cudaFuncSetAttribute(apply_sparse_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        apply_sparse_kernel<uint32_t><<<grid, SPA_THREADS, smem, st>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_mvals, d_mnorm2, d_inv_m32,
+                                                                         (int)n_ann, d_top1, d_top2, d_score1, d_score2, d_qnorm2);
+    } else {
+        SKM_CUDA_TRY(cudaFuncSetAttribute(apply_sparse_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        apply_sparse_kernel<unsigned long long><<<grid, SPA_THREADS, smem, st>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_mvals, d_mnorm2,
+                                                                                   d_inv_m32, (int)n_ann, d_top1, d_top2, d_score1, d_score2, d_qnorm2);
+    }
     SKM_LAUNCH_CHECK("apply_sparse_kernel");
     return SKM_OK;
 }

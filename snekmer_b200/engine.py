@@ -679,11 +679,13 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
 
 @dataclass
 class AnnotationCSC:
-    """k-mer-major view of an annotation slice [ann_lo, ann_lo + n_ann) with cosine weights."""
+    """k-mer-major view of an annotation slice [ann_lo, ann_lo + n_ann) of a learned matrix."""
     colptr: torch.Tensor    # int64 [S+1]
     rows: torch.Tensor      # int32 [nnz] annotation index relative to ann_lo
-    w: torch.Tensor         # float32 [nnz] = M[a, c] / ||m_a||
-    mnorm2: torch.Tensor    # float64 [n_ann]
+    mvals: torch.Tensor     # int32 [nnz] = M[a, c]
+    mnorm2: torch.Tensor    # float64 [n_ann], exact integer sums
+    inv_m32: torch.Tensor   # float32 [n_ann] = 1 / ||m_a|| (screening pass)
+    max_m: int              # largest entry
     n_ann: int
     ann_lo: int
     S: int
@@ -703,38 +705,62 @@ def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     colptr = torch.empty(S + 1, dtype=torch.int64, device=dev)
     rows = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-    w = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    mvals = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     mn2 = torch.zeros(max(n_ann, 1), dtype=torch.float64, device=dev)
-    check(lib().skm_csc_build(_ptr(keys), _ptr(vals), nnz, int(S), int(n_ann), _ptr(colptr), _ptr(rows), _ptr(w), _ptr(mn2),
-                              _ptr(ws), ws_bytes, _stream()))
-    return AnnotationCSC(colptr, rows[:nnz], w[:nnz], mn2[:n_ann], int(n_ann), int(ann_lo), int(S))
+    inv32 = torch.zeros(max(n_ann, 1), dtype=torch.float32, device=dev)
+    max_m = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_csc_build(_ptr(keys), _ptr(vals), nnz, int(S), int(n_ann), _ptr(colptr), _ptr(rows), _ptr(mvals), _ptr(mn2),
+                              _ptr(inv32), _ptr(max_m), _ptr(ws), ws_bytes, _stream()))
+    mx = int(max_m.item())
+    if mx >= 2 ** 31:
+        raise SkmError(-3, f"csc_build: an annotation count of {mx} does not fit the 32-bit CSC values")
+    return AnnotationCSC(colptr, rows[:nnz], mvals[:nnz], mn2[:n_ann], inv32[:n_ann], mx, int(n_ann), int(ann_lo), int(S))
 
 
-SPARSE_MAX_ANN = 50 * 1024
+SPARSE_MAX_ANN = 50 * 1024          # annotations per apply_sparse call with 32-bit accumulators (half with 64-bit)
 
 
-def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, csc: AnnotationCSC) -> ApplyResult:
-    """SpMM scoring of CSR queries (codes + counts, count_csr with basis=None) against one annotation slice."""
+def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, csc: AnnotationCSC,
+                 max_row_total: Optional[int] = None) -> ApplyResult:
+    """SpMM scoring of CSR queries (codes + counts, count_csr with basis=None) against one annotation slice.
+    max_row_total bounds the sum of a query's counts (default: the largest row total, one reduction); it decides
+    whether the exact integer dots fit 32-bit accumulators."""
     dev = _require_cuda(rowptr.device)
     nq = rowptr.numel() - 1
     top1 = torch.empty(nq, dtype=torch.int32, device=dev)
     top2 = torch.empty(nq, dtype=torch.int32, device=dev)
     s1 = torch.empty(nq, dtype=torch.float64, device=dev)
     s2 = torch.empty(nq, dtype=torch.float64, device=dev)
-    check(lib().skm_apply_sparse(_ptr(rowptr), _ptr(cols), _ptr(vals), nq, _ptr(csc.colptr), _ptr(csc.rows), _ptr(csc.w),
-                                 csc.n_ann, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2), None, _stream()))
+    if nq == 0 or csc.n_ann == 0:
+        return ApplyResult(top1, top2, s1, s2, None)
+    if max_row_total is None:
+        max_row_total = query_row_total_max(rowptr, vals)
+    acc_bits = 32 if csc.max_m * max(int(max_row_total), 1) < 2 ** 32 else 64
+    check(lib().skm_apply_sparse(_ptr(rowptr), _ptr(cols), _ptr(vals), nq, _ptr(csc.colptr), _ptr(csc.rows), _ptr(csc.mvals),
+                                 _ptr(csc.mnorm2), _ptr(csc.inv_m32), csc.n_ann, acc_bits, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2),
+                                 None, _stream()))
     return ApplyResult(top1, top2, s1, s2, None)
+
+
+def query_row_total_max(rowptr: torch.Tensor, vals: torch.Tensor) -> int:
+    """Largest sum of counts over a CSR row (= number of valid windows of the longest query)."""
+    if vals.numel() == 0:
+        return 0
+    csum = torch.zeros(vals.numel() + 1, dtype=torch.int64, device=vals.device)
+    torch.cumsum(vals, 0, out=csum[1:])
+    return int((csum[rowptr[1:]] - csum[rowptr[:-1]]).max().item())
 
 
 def apply_sparse_tiled(rowptr, cols, vals, keys, mvals, S: int, n_ann: int, tile: int = 8192) -> ApplyResult:
     """All annotations of a sorted COO matrix, `tile` at a time, merged with the top-2 merge
     (the same fan-in as the multi-GPU annotation sharding)."""
     idxs, scs = [], []
+    row_total = query_row_total_max(rowptr, vals)
     for a0 in range(0, max(n_ann, 1), tile):
         na = min(tile, n_ann - a0)
         if na <= 0:
             break
-        r = apply_sparse(rowptr, cols, vals, csc_build(keys, mvals, S, na, a0))
+        r = apply_sparse(rowptr, cols, vals, csc_build(keys, mvals, S, na, a0), row_total)
         i = torch.stack([r.top1.to(torch.int64), r.top2.to(torch.int64)])
         idxs.append(torch.where(i >= 0, i + a0, i))
         scs.append(torch.stack([r.score1, r.score2]))
