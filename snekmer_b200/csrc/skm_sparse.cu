@@ -155,7 +155,7 @@ __device__ __forceinline__ void top2x_push(Top2x &t, float f, unsigned long long
     }
 }
 
-constexpr int SPA_THREADS = 512;
+constexpr int SPA_THREADS = 1024;
 constexpr int SPA_EB = 512;        // query entries staged per block
 constexpr int SPA_SEG = 256;       // CSC entries per segment (8 per lane)
 
