@@ -155,6 +155,8 @@ class Ctx:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"          # keeps NCCL's version banner off stdout (one JSON line)
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
