@@ -527,7 +527,7 @@ def _load_traffic():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            TRAFFIC.update(json.load(f))
+            TRAFFIC.update({k: v for k, v in json.load(f).items() if not k.startswith("_")})
     except Exception:
         pass
 
