@@ -134,6 +134,153 @@ __global__ void __launch_bounds__(TS_THREADS) count_dense_kernel(const uint8_t *
 }
 
 // ---------------------------------------------------------------------------
+// dense, one warp per sequence (rows up to ~9 KB)
+// ---------------------------------------------------------------------------
+// The tile kernel above synchronises the whole CTA four times per tile (stage / flag / scan / flush): at K = 1000
+// it spends 28 % of its time in barriers and reaches 61 % of HBM.  Here every WARP is its own pipeline: it owns a
+// contiguous, residue-balanced range of sequences, a private counter row (the output layout) and a private symbol
+// buffer in shared memory, and only ever executes __syncwarp.  A sequence is walked in segments of 384 residues
+// (12 per lane; the mean protein fits one segment); the finished row leaves with one bulk shared->global copy.
+// ~48 independent warps per SM hide each other's load, bulk-store and shared-atomic latencies.
+constexpr int CW_WARPS = 8;
+constexpr int CW_C = 12;                          // residues per lane and segment (4 * odd: conflict-free byte reads)
+constexpr int CW_SEG = 32 * CW_C;
+constexpr int CW_SYM = ts_sym_bytes(CW_SEG);      // 480
+
+// MAP: 0 = identity basis (column = code), 1 = col_of_code staged in shared memory as uint16 columns (S <= 16384;
+// filtered codes point at a dummy counter behind the row, so the scan needs no validity test), 2 = col_of_code read
+// from global memory (large code spaces).
+// The scan is written out here rather than through ts_scan_chunk: one sequence per warp needs no boundary handling,
+// symbols are used raw (an invalid symbol's garbage digit is added and later subtracted with the same value, and no
+// window containing it is ever emitted), and the column comes from shared memory: 13 SASS instructions per residue
+// against 24 for the generic scanner.
+template <typename OutT, int MAP>
+__global__ void __launch_bounds__(32 * CW_WARPS, 6)
+count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
+                        const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
+                        const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
+                        OutT *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ uint8_t s_lut[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint16_t *s_col = reinterpret_cast<uint16_t *>(s_raw);                       // [S] when MAP == 1
+    uint8_t *mine = s_raw + map_bytes + size_t(warp) * (row_bytes + CW_SYM);
+    uint4 *s_cnt4 = reinterpret_cast<uint4 *>(mine);
+    uint8_t *s_sym = mine + row_bytes;
+    uint32_t cnt_addr = smem_addr(mine), sym_addr = smem_addr(s_sym), col_addr = smem_addr(s_col);
+    asm volatile("" : "+r"(cnt_addr), "+r"(sym_addr), "+r"(col_addr));      // keep the window addresses in registers
+    ts_lut_init(s_lut, lut);
+    if (MAP == 1)
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const int32_t c = __ldg(col_of_code + i);
+            s_col[i] = uint16_t(c >= 0 ? c : K);                                // K = the dummy counter
+        }
+    for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                                        // LUT and column map; the only CTA-wide barrier
+    // this warp's sequences: those that start in the w-th 1/W of the residue buffer
+    int64_t lo = 0, hi = 0;
+    if (lane == 0) {
+        const int64_t W = int64_t(gridDim.x) * CW_WARPS, w = int64_t(blockIdx.x) * CW_WARPS + warp;
+        const int64_t r0 = __ldg(off), span = __ldg(off + nseq) - r0;
+        lo = (w == 0) ? 0 : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * w) / W));
+        hi = (w + 1 == W) ? nseq : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * (w + 1)) / W));
+    }
+    lo = __shfl_sync(FULL, lo, 0);
+    hi = __shfl_sync(FULL, hi, 0);
+    const uint32_t uk = uint32_t(k);
+    int64_t e = (lo < hi) ? __ldg(off + lo) : 0;
+    for (int64_t s = lo; s < hi; ++s) {
+        const int64_t b = e;
+        e = __ldg(off + s + 1);
+        bool first = true;
+        uint32_t tail0 = 0, tail1 = 0;                      // the last k-1 symbols of the previous segment (k-1 <= 63)
+        for (int64_t a = b; a < e;) {
+            const int64_t a2 = min(e, (a + CW_SEG) & ~int64_t(15));
+            if (!first) {
+                if (lane < k - 1) s_sym[TS_PAD - (k - 1) + lane] = uint8_t(tail0);
+                if (lane + 32 < k - 1) s_sym[TS_PAD - (k - 1) + lane + 32] = uint8_t(tail1);
+            }
+            // stage: [a & ~15, a2) translated into s_sym[TS_PAD ...), one 16-byte vector per lane (at most 25)
+            const int64_t base = a & ~int64_t(15);
+            const int lo_i = TS_PAD + int(a - base), hi_i = lo_i + int(a2 - a);
+            const int nvec = int((a2 - base + 15) >> 4);
+            if (lane < nvec) {
+                const int64_t p = base + 16 * int64_t(lane);
+                uint4 x;
+                if (p + 16 <= nres) {
+                    x = __ldg(reinterpret_cast<const uint4 *>(res + p));
+                } else {
+                    uint32_t w4[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < 16; ++j)
+                        if (p + j < nres) w4[j >> 2] |= uint32_t(res[p + j]) << (8 * (j & 3));
+                    x = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                x.x = ts_translate4(x.x, s_lut);
+                x.y = ts_translate4(x.y, s_lut);
+                x.z = ts_translate4(x.z, s_lut);
+                x.w = ts_translate4(x.w, s_lut);
+                reinterpret_cast<uint4 *>(s_sym + TS_PAD)[lane] = x;
+            }
+            __syncwarp();
+            if (first) {                                    // nothing in front of the sequence start is a residue of it
+                for (int i = lane; i < lo_i; i += 32) s_sym[i] = uint8_t(SYM_BAD);
+                __syncwarp();
+            }
+            // scan: lane owns symbols [i0, i1), warms up on the k-1 symbols in front of them
+            const int n = hi_i - lo_i;
+            const int C = ((((n + 31) >> 5) + 3) >> 2 | 1) << 2;     // smallest 4 * odd >= ceil(n / 32)
+            const int i0 = lo_i + lane * C, i1 = min(i0 + C, hi_i);
+            if (i0 < i1) {
+                uint32_t run = 0, code = 0;
+                uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
+                for (uint32_t j = 1; j < uk; ++j, ++p) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + sy;
+                }
+                const uint32_t pend = sym_addr + uint32_t(i1);
+                const uint32_t back = uk - 1u;
+#pragma unroll 4
+                for (; p < pend; ++p) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + sy;
+                    if (run >= uk) {
+                        uint32_t col;
+                        if (MAP == 0) col = code;
+                        else if (MAP == 1) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(col) : "r"(col_addr + 2u * code));
+                        else { const int32_t c = __ldg(col_of_code + code); col = c >= 0 ? uint32_t(c) : uint32_t(K); }
+                        cnt_ops<OutT>::add(cnt_addr, col);
+                    }
+                    code -= lds_u8<0>(p - back) * pow_k1;
+                }
+            }
+            __syncwarp();
+            if (lane < k - 1) tail0 = s_sym[hi_i - (k - 1) + lane];
+            if (lane + 32 < k - 1) tail1 = s_sym[hi_i - (k - 1) + lane + 32];
+            __syncwarp();
+            first = false;
+            a = a2;
+        }
+        // ---- flush: the row is one contiguous K * sizeof(OutT) range of the output ----
+        OutT *dst = out + s * K;
+        if (bulk_ok) {
+            ts_bulk_fence();
+            __syncwarp();
+            if (lane == 0) { ts_bulk_store(dst, cnt_addr, uint32_t(K) * uint32_t(sizeof(OutT))); ts_bulk_wait_read(); }
+            __syncwarp();
+        } else {
+            __syncwarp();
+            const OutT *s_cnt = reinterpret_cast<const OutT *>(mine);
+            for (int i = lane; i < K; i += 32) dst[i] = s_cnt[i];
+            __syncwarp();
+        }
+        for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // sparse (CSR)
 // ---------------------------------------------------------------------------
 // one warp per sequence over its sorted keys: count (and optionally write) the runs
@@ -202,6 +349,38 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         set_error("skm_count_dense: K=%lld rows do not fit shared memory; use skm_count_csr", (long long)K);
         return SKM_ERR_UNSUPPORTED;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
+    // Rows up to ~9 KB: one warp per sequence with a private counter row (>= 24 warps per SM).  One extra (dummy)
+    // counter behind the row absorbs the windows whose code is filtered out of the basis.
+    const uint32_t row_bytes = uint32_t((size_t(K + 1) * out_bytes + 15) & ~size_t(15));
+    const char *force_tile = getenv("SKM_CD_TILE");
+    if (row_bytes + CW_SYM <= 9 * 1024 + 256 && K < 65535 && !(force_tile && atoi(force_tile))) {
+        const int map_mode = !d_col_of_code ? 0 : (S <= 16384 ? 1 : 2);
+        const uint32_t map_bytes = map_mode == 1 ? uint32_t((size_t(S) * 2 + 127) & ~size_t(127)) : 0u;
+        const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM);
+        int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 256));
+        if (per_sm_w > 6) per_sm_w = 6;
+        if (per_sm_w < 1) per_sm_w = 1;
+        const int grid_w = (int)std::min<int64_t>((nseq + CW_WARPS - 1) / CW_WARPS, int64_t(sm_count()) * per_sm_w);
+        const int bulk_ok = ((size_t(K) * out_bytes) % 16 == 0) ? 1 : 0;
+#define SKM_LAUNCH_DENSE_W(OUT, MAP)                                                                                 \
+    {                                                                                                                \
+        auto kern = count_dense_warp_kernel<OUT, MAP>;                                                               \
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));          \
+        kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
+                                                    d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok,    \
+                                                    (OUT *)d_counts);                                                \
+    }
+#define SKM_LAUNCH_DENSE_WM(OUT)                                                                                     \
+    { if (map_mode == 0) SKM_LAUNCH_DENSE_W(OUT, 0) else if (map_mode == 1) SKM_LAUNCH_DENSE_W(OUT, 1) else SKM_LAUNCH_DENSE_W(OUT, 2) }
+        if (out_bits == 32) SKM_LAUNCH_DENSE_WM(int32_t) else SKM_LAUNCH_DENSE_WM(uint16_t)
+#undef SKM_LAUNCH_DENSE_WM
+#undef SKM_LAUNCH_DENSE_W
+        SKM_LAUNCH_CHECK("count_dense_warp_kernel");
+        return SKM_OK;
+    }
     // Tile shape.  Many small CTAs per SM (each with its own tile in flight) hide the staging-load, barrier
     // and bulk-store latencies of one another: 128 threads, ~16 KB of counters, rows a multiple of
     // 4 (int32) / 8 (uint16) so that every tile start is 16-byte aligned and leaves as one bulk copy.
@@ -224,9 +403,6 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
     const int grid = (int)std::min<int64_t>(ntiles, int64_t(sm_count()) * per_sm);
-    cudaStream_t st = (cudaStream_t)stream;
-    uint32_t pow_k1 = 1;
-    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
 #define SKM_LAUNCH_DENSE(OUT, MAP)                                                                                   \
     {                                                                                                                \
         auto kern = count_dense_kernel<OUT, MAP>;                                                                    \
