@@ -176,6 +176,45 @@ SKM_API int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, i
                   uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
                   void *workspace, size_t workspace_bytes, skm_stream_t stream);
 
+/* ---- code spaces too large for tables (nsym^k > 2^27, up to 2^64 - 1: the alphabet/k sweep) ----------
+ * (a7) basis of one shard as a table sorted by code: distinct window codes, their occurrence counts and the
+ * position (res_base + index of the window's last residue) of their first occurrence — the dict of
+ * kmerize.smk:89-104 before filtering and ordering.  Outputs need capacity nres; *d_n_out = entries.
+ * One call handles < 2^30 residues. */
+SKM_API size_t skm_basis_sorted_local_workspace(int64_t nres);
+SKM_API int skm_basis_sorted_local(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets,
+                           int64_t nseq, const uint8_t *d_lut, int nsym, int k, int64_t res_base,
+                           uint64_t *d_codes_out, int64_t *d_counts_out, int64_t *d_first_out,
+                           int64_t *d_n_out, void *workspace, size_t workspace_bytes,
+                           skm_stream_t stream);
+/* (a7) n table entries (the concatenated tables of chunks / GPUs; merged != 0: a single table, already
+ * distinct and sorted) -> the basis: entries with equal codes are combined (sum of counts, min of first),
+ * count > min_filter kept (kmerize.smk:97-104), ordered by first position.  d_basis_out / d_basis_counts_out
+ * (nullable): codes and counts in first-occurrence order; d_sorted_codes_out + d_col_of_sorted_out: the kept
+ * codes in ascending order with the basis column of each (the lookup structure of skm_count_csr_wide /
+ * skm_codes_to_columns).  All outputs need capacity n; *d_K_out = basis size. */
+SKM_API size_t skm_basis_sorted_finalize_workspace(int64_t n);
+SKM_API int skm_basis_sorted_finalize(const uint64_t *d_codes, const int64_t *d_counts, const int64_t *d_first,
+                              int64_t n, int merged, int64_t min_filter, uint64_t *d_basis_out,
+                              int64_t *d_basis_counts_out, uint64_t *d_sorted_codes_out,
+                              int32_t *d_col_of_sorted_out, int64_t *d_K_out, void *workspace,
+                              size_t workspace_bytes, skm_stream_t stream);
+/* basis column of each code (binary search in the sorted code list), -1 when the basis does not hold it:
+ * the membership test of kmerize.smk:112-120 / the dict lookup of learn.smk:377-382 for 64-bit codes. */
+SKM_API int skm_codes_to_columns(const uint64_t *d_codes, int64_t n, const uint64_t *d_sorted_codes,
+                         const int32_t *d_col_of_sorted, int64_t K, int32_t *d_cols_out,
+                         skm_stream_t stream);
+/* (a11 at any nsym^k <= 2^64 - 1) per-sequence distinct window codes and their counts as CSR; a row's entries are
+ * ordered by code.  With a basis (d_sorted_codes, d_col_of_sorted, K) entries outside it are dropped and
+ * d_cols_out (nullable) receives the basis column of every entry; d_codes_out is nullable when d_cols_out is
+ * given.  d_rowptr int64 [nseq+1]; entry outputs need capacity nres.  One call handles < 2^30 residues. */
+SKM_API size_t skm_count_csr_wide_workspace(int64_t nres, int64_t nseq);
+SKM_API int skm_count_csr_wide(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                       const uint8_t *d_lut, int nsym, int k, const uint64_t *d_sorted_codes,
+                       const int32_t *d_col_of_sorted, int64_t K, int64_t *d_rowptr,
+                       uint64_t *d_codes_out, uint32_t *d_cols_out, int32_t *d_vals, void *workspace,
+                       size_t workspace_bytes, skm_stream_t stream);
+
 /* Annotation-major COO (key = ann * S + code) -> k-mer-major CSC for the SpMM:
  * d_colptr int64 [S+1], d_rows int32 [nnz] (annotation), d_mvals int32 [nnz] = M[a, c],
  * d_mnorm2 (nullable) = ||m_a||^2 (exact integer sum, as float64), d_inv_m32 (nullable) =

@@ -7,6 +7,8 @@ has exactly three exchange steps, each a plain collective on integer / top-2 buf
 
   basis   (kmerize.smk:89-104)   all_reduce(SUM) of per-code counts + all_reduce(MIN)
                                  of first positions (global residue positions)
+                                 (code spaces without tables: all_gather of the per-rank
+                                 (code, count, first) tables, merged by one sort)
   learn   (learn.smk:467-494)    all_reduce(SUM) of the dense count matrix / totals
   apply   (apply.smk:312-335)    when the annotation matrix is row-(annotation-)sharded:
                                  all_gather of per-shard (top1, top2, score1, score2) and a
@@ -129,6 +131,29 @@ def gather_rows(local: torch.Tensor, dst: int = 0) -> Optional[torch.Tensor]:
     if rank != dst:
         return None
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+def allgather_tables(*columns: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    """Wide-basis fan-in (kmerize.smk:89-104 over code spaces without tables): every rank contributes the
+    columns (codes, counts, first) of its local table — equal lengths on one rank, different lengths across
+    ranks — and receives the concatenation over ranks in rank order."""
+    rank, w = world()
+    if w == 1:
+        return tuple(columns)
+    dev = columns[0].device
+    n = torch.tensor([columns[0].numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(w)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    m = max(sizes + [1])
+    out = []
+    for c in columns:
+        pad = torch.zeros(m, dtype=c.dtype, device=dev)
+        pad[:c.numel()] = c
+        parts = [torch.empty_like(pad) for _ in range(w)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat([q[:sz] for q, sz in zip(parts, sizes)]))
+    return tuple(out)
 
 
 def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -768,6 +768,170 @@ def apply_sparse_tiled(rowptr, cols, vals, keys, mvals, S: int, n_ann: int, tile
 
 
 # ---------------------------------------------------------------------------
+# wide path: code spaces beyond the table limit (nsym^k > 2^27, up to 2^64 - 1) — sort-based
+# ---------------------------------------------------------------------------
+WIDE_MAX_CHUNK_RES = (1 << 30) - 16
+
+
+@dataclass
+class WideBasis:
+    """Basis over a code space too large for tables: codes in first-occurrence order plus the
+    ascending code list with the column of each entry (binary-search lookup)."""
+    alphabet: str
+    k: int
+    symbols: str
+    codes: torch.Tensor             # int64 (uint64 pattern) [K], first-occurrence order
+    counts: Optional[torch.Tensor]  # int64 [K]
+    sorted_codes: torch.Tensor      # int64 (uint64 pattern) [K], ascending (unsigned)
+    col_of_sorted: torch.Tensor     # int32 [K]
+    K: int
+
+    def codes_host(self) -> np.ndarray:
+        return self.codes.cpu().numpy().view(np.uint64)
+
+    def kmers(self) -> np.ndarray:
+        return decode_kmers(self.codes_host(), self.symbols, self.k)
+
+
+def basis_table_local(batch: SequenceBatch, alphabet: AlphabetT, k: int, res_base: int = 0,
+                      max_chunk_res: int = WIDE_MAX_CHUNK_RES) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]:
+    """(codes, counts, first) of a shard: distinct window codes sorted by code, their occurrence counts and
+    the global position of their first occurrence.  Returns a 4th item: True when the table is one merged
+    list (a single chunk), False when it is the concatenation of several chunks' tables."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    parts = []
+    for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
+        sub = batch if (lo == 0 and hi == batch.n) else _sub_batch(batch, lo, hi)
+        shift = 0 if sub is batch else (int(batch.offsets_host[lo]) & ~15)
+        n_cap = max(sub.nres, 1)
+        ws_bytes = lib().skm_basis_sorted_local_workspace(sub.nres)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        codes = torch.empty(n_cap, dtype=torch.int64, device=dev)
+        counts = torch.empty(n_cap, dtype=torch.int64, device=dev)
+        first = torch.empty(n_cap, dtype=torch.int64, device=dev)
+        dn = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(lib().skm_basis_sorted_local(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k),
+                                           int(res_base) + shift, _ptr(codes), _ptr(counts), _ptr(first), _ptr(dn), _ptr(ws),
+                                           ws_bytes, _stream()))
+        m = int(dn.item())
+        parts.append((codes[:m].clone(), counts[:m].clone(), first[:m].clone()))
+        del ws, codes, counts, first
+    if not parts:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, z.clone(), z.clone(), True
+    if len(parts) == 1:
+        return parts[0] + (True,)
+    return (torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), torch.cat([p[2] for p in parts]), False)
+
+
+def basis_table_finalize(alphabet: AlphabetT, k: int, codes: torch.Tensor, counts: torch.Tensor, first: torch.Tensor,
+                         merged: bool, min_filter: int = 0) -> WideBasis:
+    """Tables of one or more shards -> the basis in the reference's order (kmerize.smk:89-104)."""
+    dev = _require_cuda(codes.device)
+    tab = alphabet_tables(alphabet, dev)
+    n = codes.numel()
+    codes, counts, first = codes.contiguous(), counts.contiguous(), first.contiguous()
+    ws_bytes = lib().skm_basis_sorted_finalize_workspace(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = max(n, 1)
+    basis = torch.empty(cap, dtype=torch.int64, device=dev)
+    bcnt = torch.empty(cap, dtype=torch.int64, device=dev)
+    scodes = torch.empty(cap, dtype=torch.int64, device=dev)
+    scol = torch.empty(cap, dtype=torch.int32, device=dev)
+    dK = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_basis_sorted_finalize(_ptr(codes), _ptr(counts), _ptr(first), n, 1 if merged else 0, int(min_filter),
+                                          _ptr(basis), _ptr(bcnt), _ptr(scodes), _ptr(scol), _ptr(dK), _ptr(ws), ws_bytes, _stream()))
+    K = int(dK.item())
+    return WideBasis(tab.name, int(k), tab.symbols, basis[:K].clone(), bcnt[:K].clone(), scodes[:K].clone(), scol[:K].clone(), K)
+
+
+def build_basis_wide(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0) -> WideBasis:
+    """Pass 1 of the vectorize rule (kmerize.smk:89-104) for any nsym^k <= 2^64 - 1: sort-based."""
+    codes, counts, first, merged = basis_table_local(batch, alphabet, k, 0)
+    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter)
+
+
+def wide_basis_from_codes(codes: np.ndarray, alphabet: AlphabetT, k: int, device=None) -> WideBasis:
+    """Basis whose column j holds code codes[j] (uint64, distinct): a supplied / learned k-mer list."""
+    dev = _require_cuda(device)
+    tab = alphabet_tables(alphabet, dev)
+    codes = np.ascontiguousarray(codes, dtype=np.uint64)
+    order = np.argsort(codes, kind="stable")
+    d_codes = torch.from_numpy(codes.view(np.int64)).to(dev)
+    return WideBasis(tab.name, int(k), tab.symbols, d_codes, None, torch.from_numpy(codes[order].view(np.int64)).to(dev),
+                     torch.from_numpy(order.astype(np.int32)).to(dev), len(codes))
+
+
+def codes_to_columns(codes: torch.Tensor, basis: WideBasis) -> torch.Tensor:
+    """Basis column of every code (int32, -1 = not in the basis)."""
+    dev = _require_cuda(codes.device)
+    codes = codes.contiguous()
+    out = torch.empty(codes.numel(), dtype=torch.int32, device=dev)
+    check(lib().skm_codes_to_columns(_ptr(codes), codes.numel(), _ptr(basis.sorted_codes), _ptr(basis.col_of_sorted), basis.K,
+                                     _ptr(out), _stream()))
+    return out
+
+
+def count_csr_wide(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[WideBasis] = None,
+                   max_chunk_res: int = WIDE_MAX_CHUNK_RES):
+    """Per-sequence distinct k-mers and their counts for any nsym^k <= 2^64 - 1.
+    Returns (rowptr int64 [N+1], codes int64 (uint64 pattern) [nnz], cols int32 [nnz] or None, vals int32 [nnz]);
+    a row's entries are ordered by code; with a basis, entries outside it are dropped and cols holds columns."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    if basis is not None and basis.K == 0:           # nothing can match an empty basis
+        return (torch.zeros(batch.n + 1, dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.int64, device=dev),
+                torch.zeros(0, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+    rowptrs, codes_p, cols_p, vals_p = [], [], [], []
+    base_nnz = 0
+    for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
+        sub = batch if (lo == 0 and hi == batch.n) else _sub_batch(batch, lo, hi)
+        ws_bytes = lib().skm_count_csr_wide_workspace(sub.nres, sub.n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cap = max(sub.nres, 1)
+        rowptr = torch.empty(sub.n + 1, dtype=torch.int64, device=dev)
+        codes = torch.empty(cap, dtype=torch.int64, device=dev)
+        cols = torch.empty(cap, dtype=torch.int32, device=dev) if basis is not None else None
+        vals = torch.empty(cap, dtype=torch.int32, device=dev)
+        check(lib().skm_count_csr_wide(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k),
+                                       None if basis is None else _ptr(basis.sorted_codes),
+                                       None if basis is None else _ptr(basis.col_of_sorted), 0 if basis is None else basis.K,
+                                       _ptr(rowptr), _ptr(codes), _ptr(cols), _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+        nnz = int(rowptr[-1].item()) if sub.n else 0
+        rowptrs.append(rowptr[(1 if rowptrs else 0):] + base_nnz)
+        codes_p.append(codes[:nnz].clone())
+        vals_p.append(vals[:nnz].clone())
+        if cols is not None:
+            cols_p.append(cols[:nnz].clone())
+        base_nnz += nnz
+        del ws, codes, cols, vals
+    if not rowptrs:
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        e64 = torch.zeros(0, dtype=torch.int64, device=dev)
+        e32 = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, e64, (e32 if basis is not None else None), e32.clone()
+    cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
+    return cat(rowptrs), cat(codes_p), (cat(cols_p) if basis is not None else None), cat(vals_p)
+
+
+def build_basis_wide_distributed(batch: SequenceBatch, alphabet, k: int, min_filter: int = 0,
+                                 res_base: Optional[int] = None) -> WideBasis:
+    """The wide basis of the CONCATENATION of all ranks' shards, identical on every rank: local tables with
+    global first positions, all_gather of the tables, one finalisation (sort by code, sum / min, order)."""
+    from . import dist as D
+
+    if res_base is None:
+        res_base, _ = D.exclusive_prefix(batch.nres, batch.device)
+    codes, counts, first, merged = basis_table_local(batch, alphabet, k, res_base)
+    _, w = D.world()
+    if w > 1:
+        codes, counts, first = D.allgather_tables(codes, counts, first)
+        merged = False
+    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter)
+
+
+# ---------------------------------------------------------------------------
 # multi-GPU compositions (one process per GPU; collectives in dist.py)
 # ---------------------------------------------------------------------------
 def build_basis_distributed(batch: SequenceBatch, alphabet, k: int, min_filter: int = 0, res_base: Optional[int] = None) -> Basis:

@@ -32,6 +32,13 @@ def main():
     want_basis, want_tot = O.basis_codes(si, pos, code, valid, mf)
     assert np.array_equal(basis.codes_host(), want_basis), "distributed basis"
     assert np.array_equal(basis.counts.cpu().numpy(), want_tot), "distributed basis counts"
+    # the same basis through the sort-based wide path (tables all-gathered, merged by one sort), and a code
+    # space beyond the table limit
+    wb = E.build_basis_wide_distributed(batch, a, k, mf)
+    assert np.array_equal(wb.codes_host(), want_basis) and np.array_equal(wb.counts.cpu().numpy(), want_tot), "wide distributed basis"
+    si2, pos2, code2, valid2 = O.window_codes(res, off, O.build_lut(None)[0], 20, 9)
+    wb2 = E.build_basis_wide_distributed(batch, None, 9, 0)
+    assert np.array_equal(wb2.codes_host(), O.basis_codes(si2, pos2, code2, valid2, 0)[0]), "wide distributed basis 20^9"
     # learn + NCCL sum
     M, totals = E.learn_dense_distributed(batch, a, k, basis, torch.from_numpy(ann[lo:hi]), n_ann)
     C = O.count_matrix(si, code, valid, len(seqs), want_basis).astype(np.int64)

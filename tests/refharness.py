@@ -18,6 +18,7 @@ Line ranges (reference file:line):
   learn.smk:443-594    class Merge
   learn.smk:628-887    class KmerCompare (eval_apply)
   apply.smk:147-353    class KmerCompare (apply)
+  learn.smk:923-1348   class Evaluator (evaluate rule)
 """
 from __future__ import annotations
 
@@ -219,3 +220,17 @@ def run_apply_scores(workdir, nb, totals_csv, config):
         kc.match_kmer_counts_format()
         kc.cosine_similarity()
         return kc.kmer_count_totals
+
+
+def run_evaluate(workdir, score_csvs, out_conf, out_glob, base_confidence=(), modifier=1.0):
+    """learn.smk:923-1348 (class Evaluator): seq-annotation-scores CSVs -> confidence-matrix.csv and
+    global-confidence-scores.csv, optionally merged with ONE prior global-confidence file."""
+    g = _base_globals({})
+    g["params"] = SimpleNamespace(modifer=modifier)
+    src = _rule_source("learn.smk", 923, 1348)
+    with _cwd(workdir), redirect_stdout(io.StringIO()):
+        exec(compile(src, "learn.smk[923:1348]", "exec"), g)
+        ev = g["Evaluator"]([os.path.abspath(p) for p in score_csvs], out_conf, out_glob,
+                            [os.path.abspath(p) for p in base_confidence])
+        ev.execute_all()
+    return os.path.join(workdir, out_conf), os.path.join(workdir, out_glob)

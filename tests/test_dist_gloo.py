@@ -109,6 +109,20 @@ def _worker(rank, world, port, tmp):
         tot = torch.tensor([int(rv.sum()), int(cnt.sum())])
         dist.all_reduce(tot)
         assert tot[0].item() == tot[1].item()                 # nothing lost, nothing duplicated
+        # ---- wide basis fan-in: all_gather of per-rank (code, count, first) tables, merged by code -------------
+        lc, li, lcnt = np.unique(code[valid], return_index=True, return_counts=True)
+        lfirst = ((off[lo:hi + 1] - off[lo])[si[valid]] + pos[valid] + base)[li]
+        gc, gn, gf = D.allgather_tables(torch.from_numpy(lc.astype(np.int64)), torch.from_numpy(lcnt.astype(np.int64)),
+                                        torch.from_numpy(lfirst.astype(np.int64)))
+        assert gc.numel() == gn.numel() == gf.numel()
+        mc, inv = np.unique(gc.numpy(), return_inverse=True)
+        msum = np.zeros(len(mc), np.int64)
+        np.add.at(msum, inv, gn.numpy())
+        mfirst = np.full(len(mc), np.iinfo(np.int64).max)
+        np.minimum.at(mfirst, inv, gf.numpy())
+        keep2 = msum > mf
+        wide_basis = mc[keep2][np.argsort(mfirst[keep2], kind="stable")].astype(np.uint64)
+        assert np.array_equal(wide_basis, want_basis)
         # ---- query-sharded outputs concatenated in rank order ---------------------------------
         mine = torch.arange(lo, hi, dtype=torch.int64).reshape(-1, 1)
         allrows = D.gather_rows(mine, dst=0)
