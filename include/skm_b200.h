@@ -301,6 +301,31 @@ SKM_API int skm_scatter_add_i64(const int64_t *d_src, int64_t rows, int64_t cols
                         int64_t *d_dst, int64_t dst_rows, int64_t dst_cols,
                         skm_stream_t stream);
 
+/* ---- confidence evaluation (rule `evaluate`, class Evaluator, learn.smk:923-1348) ----------------------
+ * Read-back of a score matrix (learn.smk:964-981): per row of d_scores float64 [nq, n_ann] with NaN holes,
+ * the column of the maximum (NaN skipped, first maximum = idxmax) and the two largest values; rows without
+ * values give -1 / NaN. */
+SKM_API int skm_top2_rows_f64(const double *d_scores, int64_t nq, int64_t n_ann, int32_t *d_top1,
+                      int32_t *d_top2, double *d_score1, double *d_score2, skm_stream_t stream);
+/* Difference bin of every query, 100 * -(round(score2 - score1, 2)) in 0..100 (255 when it is undefined:
+ * no prediction, NaN, outside the 101 values of learn.smk:1063), written to d_bin_out (nullable), and — when
+ * d_class is given — the crosstabs of learn.smk:1052-1061: d_hist_true / d_hist_false int64 [n_ann, 101]
+ * += 1 at (top1, bin) for rows of class 1 (Known, True) / 2 (Known, False); class 0 rows are skipped.
+ * The histograms are accumulated (not cleared), so files and shards add up. */
+SKM_API int skm_confidence_hist(const int32_t *d_top1, const double *d_score1, const double *d_score2,
+                        const uint8_t *d_class, int64_t nq, int64_t n_ann, int64_t *d_hist_true,
+                        int64_t *d_hist_false, uint8_t *d_bin_out, skm_stream_t stream);
+
+/* ---- FASTA ingest (host cores, no device work): Bio.SeqIO.parse(f, "fasta") as kmerize.smk:90-129 uses it ----
+ * text = the (decompressed) file in host memory.  A record starts at a '>' in column 0; id = the title up to its
+ * first whitespace; sequence = the record's lines, each right-stripped, joined, blanks and CR removed.
+ * skm_fasta_scan sizes the outputs; skm_fasta_pack writes residues [nres] back to back, offsets int64 [nseq+1],
+ * the id bytes back to back and id_offsets int64 [nseq+1].  threads <= 0: all hardware threads. */
+SKM_API int skm_fasta_scan(const uint8_t *text, int64_t nbytes, int threads, int64_t *nseq_out,
+                   int64_t *nres_out, int64_t *idbytes_out);
+SKM_API int skm_fasta_pack(const uint8_t *text, int64_t nbytes, int threads, uint8_t *residues_out,
+                   int64_t *offsets_out, uint8_t *ids_out, int64_t *id_offsets_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,8 +56,9 @@ def define_output_dir(alphabet, k: int, nested: bool = False) -> str:
 # FASTA -> packed buffer
 # ---------------------------------------------------------------------------
 def read_fasta(path: str) -> Tuple[List[str], List[str]]:
-    """(ids, sequences).  id = header up to the first whitespace, sequence = the
-    record's lines joined (Bio.SeqIO "fasta" semantics); .gz files are read transparently."""
+    """(ids, sequences).  id = header up to the first whitespace, sequence = the record's lines, each
+    right-stripped, joined, blanks and CR removed (Bio.SeqIO "fasta" semantics: SimpleFastaParser);
+    .gz files are read transparently."""
     opener = gzip.open if str(path).endswith(".gz") else open
     ids: List[str] = []
     seqs: List[str] = []
@@ -67,16 +68,59 @@ def read_fasta(path: str) -> Tuple[List[str], List[str]]:
         for line in f:
             if line.startswith(">"):
                 if started:
-                    seqs.append("".join(parts))
+                    seqs.append("".join(parts).replace(" ", "").replace("\r", ""))
                 head = line[1:].split(None, 1)
                 ids.append(head[0] if head else "")
                 parts = []
                 started = True
             elif started:
-                parts.append(line.strip())
+                parts.append(line.rstrip())
     if started:
-        seqs.append("".join(parts))
+        seqs.append("".join(parts).replace(" ", "").replace("\r", ""))
     return ids, seqs
+
+
+def read_fasta_packed(path: str, threads: int = 0, pinned: bool = False):
+    """FASTA file -> (ids list[str], residues uint8 [R], offsets int64 [N+1]) with the native multithreaded
+    parser (skm_fasta_scan / skm_fasta_pack; same record semantics as read_fasta).  The arrays have the layout
+    of engine.SequenceBatch; with pinned=True residues / offsets are views of pinned torch tensors, ready for an
+    asynchronous upload."""
+    import ctypes as C
+
+    from ._native import check, lib
+
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
+        text = f.read()
+    return parse_fasta_bytes(text, threads, pinned)
+
+
+def parse_fasta_bytes(text: bytes, threads: int = 0, pinned: bool = False):
+    import ctypes as C
+
+    from ._native import check, lib
+
+    n = len(text)
+    buf = np.frombuffer(text, dtype=np.uint8)
+    tp = buf.ctypes.data if n else None
+    nseq, nres, idb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    check(lib().skm_fasta_scan(tp, n, int(threads), C.byref(nseq), C.byref(nres), C.byref(idb)))
+    nseq, nres, idb = nseq.value, nres.value, idb.value
+    if pinned:
+        import torch
+
+        residues = torch.empty(max(nres, 1), dtype=torch.uint8, pin_memory=True).numpy()[:nres]
+        offsets = torch.empty(nseq + 1, dtype=torch.int64, pin_memory=True).numpy()
+    else:
+        residues = np.empty(nres, dtype=np.uint8)
+        offsets = np.empty(nseq + 1, dtype=np.int64)
+    ids_buf = np.empty(idb, dtype=np.uint8)
+    id_off = np.empty(nseq + 1, dtype=np.int64)
+    check(lib().skm_fasta_pack(tp, n, int(threads), residues.ctypes.data if nres else None, offsets.ctypes.data,
+                               ids_buf.ctypes.data if idb else None, id_off.ctypes.data))
+    raw = ids_buf.tobytes()
+    ids = [raw[id_off[i]:id_off[i + 1]].decode("utf-8", "replace") for i in range(nseq)]
+    return ids, residues, offsets
 
 
 def pack_sequences(seqs) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -6,6 +6,7 @@ apply rules on the batch GPU API (same inputs, same output files).
   merge_rule       rules/learn.smk:443-594   (class Merge)
   eval_apply_rule  rules/learn.smk:628-887   (class KmerCompare of the learn workflow)
   apply_rule       rules/apply.smk:147-353   (class KmerCompare of the apply workflow)
+  evaluate_rule    rules/learn.smk:923-1348  (class Evaluator; device side in confidence.py)
 
 Each rule has an in-memory core (``vectorize_records``, ``learn_counts``,
 ``merge_tables``, ``cosine_top2``) that returns arrays, and a thin file layer
@@ -62,10 +63,17 @@ def _reduced_strings(batch: E.SequenceBatch, alphabet) -> List[str]:
 
 def vectorize_records(ids: Sequence[str], seqs: Sequence[str], alphabet, k: int, min_filter: int = 0,
                       kmerbasis: Optional[Sequence[str]] = None) -> VectorizeResult:
-    """Both passes of the vectorize rule for one FASTA shard held in memory."""
-    seqs = [str(s) for s in seqs]
-    batch = E.SequenceBatch.from_strings(seqs)
-    lengths = np.array([len(s) for s in seqs], dtype=np.int64)
+    """Both passes of the vectorize rule for one FASTA shard held in memory as strings."""
+    residues, offsets = E.SequenceBatch.pack_host([str(s) for s in seqs])
+    return vectorize_packed(ids, residues, offsets, alphabet, k, min_filter, kmerbasis)
+
+
+def vectorize_packed(ids: Sequence[str], residues: np.ndarray, offsets: np.ndarray, alphabet, k: int, min_filter: int = 0,
+                     kmerbasis: Optional[Sequence[str]] = None, pinned: bool = False) -> VectorizeResult:
+    """Both passes of the vectorize rule for a packed shard (io.read_fasta_packed's layout): no per-record
+    Python objects on the way to the device."""
+    batch = E.SequenceBatch.from_packed(residues, offsets, pinned=pinned)
+    lengths = np.diff(np.asarray(offsets, dtype=np.int64))
     if kmerbasis is not None:                       # basis.txt branch, kmerize.smk:72-78
         kmerlist = list(kmerbasis)
         counts = E.count_over_kmers(batch, alphabet, k, kmerlist)
@@ -79,9 +87,9 @@ def vectorize_records(ids: Sequence[str], seqs: Sequence[str], alphabet, k: int,
 def vectorize_rule(fasta: str, out_npz: str, out_kmerobj: Optional[str], alphabet, k: int, min_filter: int = 0,
                    basis_file: Optional[str] = None) -> VectorizeResult:
     kmer = KmerVec(alphabet=alphabet, k=k)
-    ids, seqs = skio.read_fasta(fasta)
+    ids, residues, offsets = skio.read_fasta_packed(fasta, pinned=True)      # native multithreaded parser
     kmerbasis = skio.read_kmers(basis_file) if (basis_file and os.path.exists(basis_file)) else None
-    r = vectorize_records(ids, seqs, alphabet, k, 0 if kmerbasis is not None else min_filter, kmerbasis)
+    r = vectorize_packed(ids, residues, offsets, alphabet, k, 0 if kmerbasis is not None else min_filter, kmerbasis, pinned=True)
     kmer.set_kmer_set(r.kmerlist)
     np.savez_compressed(out_npz, kmerlist=r.kmerlist, ids=r.ids, seqs=r.seqs, vecs=r.vecs(), lengths=r.lengths)
     if out_kmerobj:
@@ -401,3 +409,38 @@ def apply_rule(npz: str, counts_csv: str, confidence_csv: str, out_summary: str,
         "Confidence": pa.array(confidence, from_pandas=True),      # NaN -> null, like DataFrame.map misses
     })
     return ScoreResult(ids, anns, top1, r.top2.cpu().numpy(), s1, s2, r.scores.cpu().numpy() if r.scores is not None else None)
+
+
+# ---------------------------------------------------------------------------
+# evaluate (Evaluator)
+# ---------------------------------------------------------------------------
+def evaluate_rule(score_csvs: Sequence[str], out_conf: str, out_glob: str, base_confidence: Sequence[str] = (),
+                  modifier: float = 1.0):
+    """learn.smk:897-1360: seq-annotation-scores files -> confidence-matrix.csv + global-confidence-scores.csv
+    (optionally merged with ONE prior global-confidence file, weight modifier = conf_weight_modifier)."""
+    from .confidence import Evaluator
+
+    ev = Evaluator(list(score_csvs), out_conf, out_glob, list(base_confidence), modifier=modifier)
+    return ev.execute_all()
+
+
+def evaluate_results(results: Sequence[ScoreResult], out_conf: Optional[str] = None, out_glob: Optional[str] = None,
+                     base_confidence: Sequence[str] = (), modifier: float = 1.0):
+    """The same evaluation fed by eval_apply_rule's in-memory results (top-2 per row): no Q x A file is read back."""
+    from . import confidence as CF
+
+    dev = E._require_cuda()
+    acc = CF.ConfidenceAccumulator()
+    for r in results:
+        res = E.ApplyResult(torch.from_numpy(np.ascontiguousarray(r.top1, dtype=np.int32)).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(r.top2, dtype=np.int32)).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(r.score1, dtype=np.float64)).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(r.score2, dtype=np.float64)).to(dev))
+        acc.add(res, r.rows, r.annotations)
+    prior = CF.read_global_confidence(str(base_confidence[0])) if len(base_confidence) == 1 else None
+    out = acc.finalize(prior, modifier)
+    if out_glob:
+        CF.write_global_confidence(out_glob, out)
+    if out_conf:
+        CF.write_confidence_matrix(out_conf, out)
+    return out

@@ -156,3 +156,55 @@ def test_csr_matches_dense():
         nz = np.flatnonzero(C[r])
         assert np.array_equal(nz.astype(np.uint64), ccodes[rowptr[r]:rowptr[r + 1]])
         assert np.array_equal(C[r, nz], ccnt[rowptr[r]:rowptr[r + 1]])
+
+
+# ---------------------------------------------------------------------------
+# confidence evaluation (learn.smk:923-1348): oracle/skm_evaluator.py pinned on files written by the reference
+# ---------------------------------------------------------------------------
+def _eval_fixture():
+    import csv
+    import io
+
+    from oracle import skm_evaluator as EV
+
+    d = np.load(os.path.join(GOLDEN, "eval_confidence.npz"))
+    txt = lambda k: bytes(d[k]).decode()
+
+    def scores(t):
+        r = list(csv.reader(io.StringIO(t)))
+        ix = r[0].index("__index_level_0__")
+        cols = [c for i, c in enumerate(r[0]) if i != ix]
+        S = np.array([[float(v) if v != "" else np.nan for i, v in enumerate(x) if i != ix] for x in r[1:]])
+        return S, [x[ix] for x in r[1:]], cols
+
+    def glob(t):
+        r = list(csv.reader(io.StringIO(t)))
+        assert r[0] == ["Difference", "confidence", "weight", "sum"]
+        return [x[0] for x in r[1:]], np.array([[float(v) if v != "" else np.nan for v in x] for x in r[1:]])
+
+    def conf(t):
+        r = list(csv.reader(io.StringIO(t)))
+        assert r[0][-1] == "Prediction"
+        rows = [x[-1] for x in r[1:]]
+        return r[0][:-1], rows, np.array([[float(v) if v != "" else np.nan for v in x[:-1]] for x in r[1:]]).reshape(len(rows), -1)
+
+    return EV, txt, scores, glob, conf
+
+
+@pytest.mark.parametrize("name,files,prior,mod", [("one", ["synA"], None, 1.0), ("two", ["synA", "synB"], None, 1.0),
+                                                  ("tricky", ["tricky"], None, 1.0), ("tricky_first", ["tricky", "synA"], None, 1.0),
+                                                  ("prior", ["synB"], "one", 0.5)])
+def test_evaluator_oracle_matches_reference_files(name, files, prior, mod):
+    EV, txt, scores, glob, conf = _eval_fixture()
+    pr = None
+    if prior:
+        _, a = glob(txt(prior + "_glob"))
+        pr = dict(confidence=a[:, 1], weight=a[:, 2], sum=a[:, 3])
+    r = EV.evaluate([scores(txt(f + "_csv")) for f in files], pr, mod)
+    lab, g = glob(txt(name + "_glob"))
+    hdr, rows, c = conf(txt(name + "_conf"))
+    assert len(lab) == 101 and lab[0] == ("-0.0" if r["zero_negative"] else "0.0") and hdr[0] == lab[0]
+    assert [float(x) for x in lab[1:]] == list(EV.POSSIBLE[1:])
+    assert np.array_equal(g[:, 1], r["confidence"], equal_nan=True)          # bit-exact float64
+    assert np.array_equal(g[:, 2], r["weight"]) and np.array_equal(g[:, 3], r["sum"])
+    assert rows == r["rows"] and np.array_equal(c, r["ratio"], equal_nan=True)
