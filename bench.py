@@ -17,8 +17,8 @@ finalisation (first-occurrence order), pass 2 dense per-sequence counts as int32
   cpu_baseline  the oracle port (numpy restatement of the reference) on the host cores, on a
              bounded sample of the same workload
 
---workload learn | apply | apply_sparse run the C3 / C4 shaped paths (sparse sort-based learn,
-tcgen05 dense scoring, SpMM scoring) with the same JSON contract; they are not the driver's line.
+--workload learn | apply | apply_sparse | sweep run the C3 / C4 / C5 shaped paths (sparse sort-based learn,
+tcgen05 dense scoring, SpMM scoring, alphabet / k sweep) with the same JSON contract; they are not the driver's line.
 `--impl reference` times only the CPU arm (rank 0), same JSON shape.
 """
 import argparse
@@ -520,6 +520,79 @@ def run_apply_sparse(ctx, args):
     return line, None
 
 
+SWEEP_POINTS = [("hydro", 8), ("hydro", 14), ("solvacc", 8), ("solvacc", 14), ("standard", 4), ("standard", 8), ("standard", 12),
+                ("miqs", 3), ("miqs", 6), ("miqs", 10), ("miqs", 14), (None, 2), (None, 5), (None, 8), (None, 11), (None, 14)]
+
+
+def run_sweep(ctx, args):
+    """C5: alphabet / k sweep (2..20 letters, k = 2..14).  One step = every point once: basis + per-sequence
+    counts through engine.vectorize (table kernels up to 2^27 codes, sort-based wide path beyond)."""
+    torch = ctx.torch
+    from snekmer_b200 import engine as E
+
+    res_np, offsets = synth_proteins(args.nseq, 5 + 1000 * ctx.rank)
+    nres = int(offsets[-1])
+    batch = E.SequenceBatch.from_packed(res_np, offsets, ctx.dev)
+    points = SWEEP_POINTS
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in points]
+    per_ms = [[] for _ in points]
+    info = [None] * len(points)
+
+    def step(timed):
+        for i, (a, k) in enumerate(points):
+            if timed:
+                ev[i][0].record()
+            v = E.vectorize(batch, a, k)
+            if timed:
+                ev[i][1].record()
+            info[i] = (v.path, v.K, int(v.vals.numel()) if v.vals is not None else None)
+            del v
+        if timed:
+            torch.cuda.synchronize()
+            for i in range(len(points)):
+                per_ms[i].append(ev[i][0].elapsed_time(ev[i][1]))
+
+    total_ms, clocks = ctx.timed(step, args.steps, args.warmup)
+    (total_ms,) = ctx.max_over_ranks([total_ms])
+    ms = total_ms / args.steps
+    pts = []
+    alg_total = 0
+    for i, (a, k) in enumerate(points):
+        tab = E.alphabet_tables(a, ctx.dev)
+        path, K, nnz = info[i]
+        m = float(np.mean(per_ms[i]))
+        # SURVEY 8(d): B_vec (dense: R + 8(N+1) + 4NK; sparse: R + 16(N+1) + 12 nnz) + B_basis (R + 8(N+1) + 24 K)
+        vec_b = nres + 8 * (batch.n + 1) + (4 * batch.n * K if path == "dense" else 8 * (batch.n + 1) + (12 if path == "csr" else 16) * nnz)
+        alg = vec_b + nres + 8 * (batch.n + 1) + 24 * K
+        alg_total += alg
+        pts.append({"alphabet": str(a), "nsym": tab.nsym, "k": k, "log2_space": round(k * float(np.log2(tab.nsym)), 1), "path": path, "K": K,
+                    "nnz": nnz, "ms": m, "seq_per_s": ctx.world * args.nseq / (m * 1e-3), "hbm_frac": alg / (m * 1e-3) / 1e9 / peaks()[0]})
+    peak, peak_kind = peaks()
+    line = {"metric": "sequences/sec vectorize (alphabet/k sweep)", "value": ctx.world * args.nseq * len(points) / (ms * 1e-3),
+            "unit": "sequences/s", "n_gpus": ctx.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "uint32/uint64 codes, int32 counts", "data": "synthetic",
+            "config": {"workload": f"C5: {len(points)} (alphabet, k) points x {args.nseq} proteins/GPU; value = point-vectorisations of a sequence per second",
+                       "points": pts, "l2": "inputs 0.35 GB x N/1e6, keys 8-16 B per residue: larger than L2",
+                       "parallelism": f"sequence-sharded x{ctx.world}, no collective"},
+            "clocks": clocks, "gpu_launches": sum(12 if p["path"] == "dense" else 25 for p in pts) * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "whole sweep step (table kernels + radix / segmented sorts)", "achieved": alg_total / (ms * 1e-3) / 1e9,
+                         "peak": peak, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "unit": "GB/s",
+                         "frac": alg_total / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg_total, "kernel_ms": ms, "traffic": None,
+                         "note": "per-point fractions in config.points; the sort-based points move 10-20 x their algorithmic bytes"}}
+
+    def cpu(sample):
+        from oracle import cpu_baseline
+        n = min(max(sample // 8, 1000), len(offsets) - 1)
+        out = []
+        for a, k in [("miqs", 6), (None, 8), (None, 14)]:
+            r = cpu_baseline.vectorize_sparse_sample(res_np[:offsets[n]], offsets[:n + 1], a, k)
+            out.append({"alphabet": str(a), "k": k, "seq_per_s": r["nseq"] / r["seconds"], "K": r["K"]})
+        v = len(out) / sum(1.0 / o["seq_per_s"] for o in out)
+        return {"value": v, "unit": "sequences/s", "cores": r["cores"], "kind": "port",
+                "sample": f"first {n} sequences, 3 of the sweep points (harmonic mean), numpy oracle port, one process per shard", "points": out}
+    return line, cpu
+
+
 TRAFFIC = {}     # kernel -> dram bytes per launch from the committed `ncu --set full` capture (profiles/), else absent
 
 
@@ -565,7 +638,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="vectorize", choices=["vectorize", "learn", "apply", "apply_sparse"],
+    ap.add_argument("--workload", default="vectorize", choices=["vectorize", "learn", "apply", "apply_sparse", "sweep"],
                     help="vectorize = the headline (BASELINE.json config C2); the others are the C3 / C4 shaped paths")
     ap.add_argument("--nseq", type=int, default=0, help="sequences per GPU (default per workload)")
     ap.add_argument("--n-ann", type=int, default=50000)
@@ -575,13 +648,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if not args.nseq:
-        args.nseq = {"vectorize": 1_000_000, "learn": 1_250_000, "apply": 1_000_000, "apply_sparse": 200_000}[args.workload]
+        args.nseq = {"vectorize": 1_000_000, "learn": 1_250_000, "apply": 1_000_000, "apply_sparse": 200_000, "sweep": 200_000}[args.workload]
     if args.impl == "reference":
         reference_arm(args)
         return
     _load_traffic()
     ctx = Ctx(args)
-    line, cpu = {"vectorize": run_vectorize, "learn": run_learn, "apply": run_apply, "apply_sparse": run_apply_sparse}[args.workload](ctx, args)
+    line, cpu = {"vectorize": run_vectorize, "learn": run_learn, "apply": run_apply, "apply_sparse": run_apply_sparse, "sweep": run_sweep}[args.workload](ctx, args)
     if ctx.rank == 0:
         if not args.no_cpu and ctx.world == 1 and cpu is not None:
             ncores = os.cpu_count() or 1

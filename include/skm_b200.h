@@ -301,6 +301,19 @@ SKM_API int skm_scatter_add_i64(const int64_t *d_src, int64_t rows, int64_t cols
                         int64_t *d_dst, int64_t dst_rows, int64_t dst_cols,
                         skm_stream_t stream);
 
+/* (a11) per-sequence counts as CSR WITHOUT a device-wide sort: a warp scans one sequence, sorts its window keys in
+ * shared memory (bitonic network) and run-length encodes them; longer sequences get a CTA.  Same results as
+ * skm_count_csr (key_bits = 32: keys = codes, or basis columns when d_col_of_code [S] is given; rows sorted by key)
+ * and skm_count_csr_wide (key_bits = 64: keys = codes; with d_sorted_codes / d_col_of_sorted / K entries outside
+ * the basis are dropped and d_cols_out (nullable) receives their columns).  d_keys_out: uint32 / uint64 [nres]
+ * (nullable when d_cols_out is given).  max_len = longest sequence (<= 0: unknown).  < 2^30 residues per call. */
+SKM_API size_t skm_count_csr_sorted_workspace(int64_t nres, int64_t nseq, int64_t max_len, int key_bits);
+SKM_API int skm_count_csr_sorted(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                         const uint8_t *d_lut, int nsym, int k, int key_bits, const int32_t *d_col_of_code,
+                         int64_t S, const uint64_t *d_sorted_codes, const int32_t *d_col_of_sorted, int64_t K,
+                         int64_t max_len, int64_t *d_rowptr, void *d_keys_out, uint32_t *d_cols_out,
+                         int32_t *d_vals, void *workspace, size_t workspace_bytes, skm_stream_t stream);
+
 /* ---- confidence evaluation (rule `evaluate`, class Evaluator, learn.smk:923-1348) ----------------------
  * Read-back of a score matrix (learn.smk:964-981): per row of d_scores float64 [nq, n_ann] with NaN holes,
  * the column of the maximum (NaN skipped, first maximum = idxmax) and the two largest values; rows without

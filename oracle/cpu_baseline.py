@@ -75,6 +75,44 @@ def vectorize_sample(residues, offsets, alphabet, k, workers=None, min_filter=0)
     return {"seconds": dt, "nseq": n, "cores": len(shards), "K": int(len(basis)), "checksum": int(sum(tot))}
 
 
+def _phase2_sparse(args):
+    lo, hi, basis_sorted = args
+    res, off, _ = _shard(lo, hi)
+    si, pos, code, valid = O.window_codes(res, off, _G["lut"], len(_G["syms"]), _G["k"])
+    j = np.searchsorted(basis_sorted, code)
+    j[j >= len(basis_sorted)] = max(len(basis_sorted) - 1, 0)
+    keep = valid & (basis_sorted[j] == code) if len(basis_sorted) else np.zeros_like(valid)
+    rowptr, codes, cnt = O.count_csr(si, code, keep, hi - lo)
+    return int(cnt.sum())
+
+
+def vectorize_sparse_sample(residues, offsets, alphabet, k, workers=None, min_filter=0):
+    """vectorize_sample for bases too large for dense rows: phase 2 produces per-sequence (code, count) lists
+    (the alphabet / k sweep).  Returns dict(seconds, nseq, cores, K)."""
+    n = len(offsets) - 1
+    workers = max(1, min(workers or os.cpu_count() or 1, 64, n))
+    cuts = np.linspace(0, n, workers + 1).astype(np.int64)
+    shards = [(int(cuts[i]), int(cuts[i + 1])) for i in range(workers) if cuts[i + 1] > cuts[i]]
+    ctx = get_context("fork")
+    _init(residues, offsets, alphabet, k)
+    with ctx.Pool(len(shards)) as pool:
+        pool.map(_phase1, shards[:1])
+        t0 = time.perf_counter()
+        parts = pool.map(_phase1, shards)
+        codes = np.concatenate([p[0] for p in parts])
+        first = np.concatenate([p[1] for p in parts])
+        cnt = np.concatenate([p[2] for p in parts])
+        order = np.argsort(codes, kind="stable")
+        codes, first, cnt = codes[order], first[order], cnt[order]
+        starts = np.flatnonzero(np.r_[True, codes[1:] != codes[:-1]]) if len(codes) else np.zeros(0, np.int64)
+        ucodes = codes[starts]
+        ucnt = np.add.reduceat(cnt, starts) if len(starts) else cnt[:0]
+        basis_sorted = ucodes[ucnt > min_filter]
+        tot = pool.map(_phase2_sparse, [(lo, hi, basis_sorted) for lo, hi in shards])
+        dt = time.perf_counter() - t0
+    return {"seconds": dt, "nseq": n, "cores": len(shards), "K": int(len(basis_sorted)), "checksum": int(sum(tot))}
+
+
 # ---------------------------------------------------------------------------
 # learn / apply samples (same fan-out: one process per shard)
 # ---------------------------------------------------------------------------

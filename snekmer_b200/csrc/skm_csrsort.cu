@@ -1,0 +1,440 @@
+// skm_csrsort.cu — per-sequence k-mer counts as CSR without a device-wide sort (kernel (b), sparse form).
+//
+// The first version of skm_count_csr wrote one key per residue to HBM and ran cub::DeviceSegmentedSort over the
+// sequences: proteins (mean 350 residues) fall into CUB's "large segment" kernel, one 256-thread CTA per protein,
+// and the step ran at 4 G keys/s — 15 ms per 200 k proteins, 1 % of the HBM roofline.  Here a WARP owns a sequence
+// from the residue bytes to its finished CSR row:
+//   scan     residues -> LUT -> symbols in the warp's shared buffer -> rolling codes (the count_dense_warp_kernel
+//            scanner); the key of every window (code, or basis column) goes to the warp's key buffer in shared memory;
+//   sort     bitonic network over the n keys in shared memory, all compare-exchanges ascending (flip formulation),
+//            so n need not be a power of two: partners at or beyond n act as +infinity;
+//   encode   run heads -> (key, run length) written to the sequence's own slots of a temporary CSR
+//            (tmp[off[s] + j]: a sequence never has more distinct k-mers than residues), distinct count -> rowcount.
+// A scan of rowcount gives rowptr and a copy kernel compacts the rows.  HBM traffic: residues once, 8-12 B per
+// distinct entry written, read and written again.  Sequences longer than the warp buffer (1024 windows; ~2 % of
+// UniRef-like proteins) are queued and handled by one CTA each (8192 keys in shared memory; beyond that the network
+// runs on a global scratch row).
+// 64-bit keys (code spaces up to 2^64 - 1) use the same kernel; with a basis given as a sorted code list the head of
+// every run is looked up (bucketed binary search) and runs outside the basis are dropped.
+#include <cub/cub.cuh>
+
+#include "skm_common.cuh"
+#include "skm_tile.cuh"
+
+namespace skm {
+
+constexpr int CS_C = 12;                       // residues per thread and segment (4 * odd)
+constexpr int CS_WARPS = 8;                    // warps (= sequences in flight) per CTA of the warp kernel
+constexpr int CS_KCAP_W = 1024;                // keys per warp buffer
+constexpr int CS_KCAP_C = 8192;                // keys per CTA buffer of the long-sequence kernel
+constexpr int CS_LONG_THREADS = 256;
+
+template <typename T> struct key_none;
+template <> struct key_none<uint32_t> { static constexpr uint32_t v = 0xFFFFFFFFu; };
+template <> struct key_none<uint64_t> { static constexpr uint64_t v = ~0ull; };
+
+template <int GT> __device__ __forceinline__ void gsync() { if (GT == 32) __syncwarp(); else __syncthreads(); }
+
+// basis lookup: sorted code list + column of each entry; `bucket` (nullable) = start index of every 2^shift-wide
+// code range, so the binary search runs over a handful of entries
+struct SortedBasis {
+    const uint64_t *codes;
+    const int32_t *col;
+    const uint32_t *bucket;     // [nbucket + 1]
+    int64_t K;
+    int shift;
+};
+__device__ __forceinline__ int32_t sorted_lookup(const SortedBasis &b, uint64_t code) {
+    int64_t lo = 0, hi = b.K;
+    if (b.bucket) {
+        const uint64_t q = code >> b.shift;
+        lo = __ldg(b.bucket + q);
+        hi = __ldg(b.bucket + q + 1);
+    }
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(b.codes + mid) < code) lo = mid + 1; else hi = mid;
+    }
+    return (lo < b.K && __ldg(b.codes + lo) == code) ? __ldg(b.col + lo) : -1;
+}
+
+// ascending bitonic network over keys[0, n) by a group of GT threads (g = thread index in the group)
+template <typename KeyT, int GT>
+__device__ __forceinline__ void group_sort(KeyT *keys, int n, int g) {
+    if (n < 2) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        const int hk = k >> 1;
+        // flip step: i in the lower half of its k-block pairs with the mirrored element of the upper half
+        for (int t = g; t < (P >> 1); t += GT) {
+            const int blk = t / hk, r = t - blk * hk;
+            const int i = blk * k + r, j = blk * k + (k - 1 - r);
+            if (j < n) {
+                const KeyT a = keys[i], b = keys[j];
+                if (b < a) { keys[i] = b; keys[j] = a; }
+            }
+        }
+        gsync<GT>();
+        for (int d = hk >> 1; d > 0; d >>= 1) {
+            for (int t = g; t < (P >> 1); t += GT) {
+                const int i = ((t & ~(d - 1)) << 1) | (t & (d - 1)), j = i + d;
+                if (j < n) {
+                    const KeyT a = keys[i], b = keys[j];
+                    if (b < a) { keys[i] = b; keys[j] = a; }
+                }
+            }
+            gsync<GT>();
+        }
+    }
+}
+
+// MODE 0: key = code.  MODE 1: key = col_of_code[code] (table basis; filtered codes never enter).
+// MODE 2: key = code, heads looked up in a SortedBasis (runs outside it dropped, column written to tmp_cols).
+// LONG = false: one warp per sequence, sequences with more than kcap windows are appended to long_list.
+// LONG = true : one CTA per queued sequence.
+template <typename KeyT, int MODE, bool LONG>
+__global__ void __launch_bounds__(LONG ? CS_LONG_THREADS : 32 * CS_WARPS)
+csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
+                const uint8_t *__restrict__ lut, KeyT nsym, int k, KeyT pow_k1, const int32_t *__restrict__ col_of_code,
+                SortedBasis sb, int kcap, int64_t *long_list, unsigned long long *n_long, KeyT *gscratch, int64_t gscratch_stride,
+                KeyT *__restrict__ tmp_keys, int32_t *__restrict__ tmp_cols, int32_t *__restrict__ tmp_vals,
+                int64_t *__restrict__ rowcount) {
+    constexpr int GT = LONG ? CS_LONG_THREADS : 32;
+    constexpr int SEG = GT * CS_C;
+    constexpr int SYM_BYTES = ts_sym_bytes(SEG);
+    constexpr KeyT NONE = key_none<KeyT>::v;
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ uint8_t s_lut[256];
+    __shared__ int s_wcnt[CS_LONG_THREADS / 32];
+    const int grp = LONG ? 0 : (threadIdx.x >> 5);
+    const int g = LONG ? int(threadIdx.x) : int(threadIdx.x & 31);
+    const int lane = threadIdx.x & 31;
+    uint8_t *mine = s_raw + size_t(grp) * (size_t(kcap) * sizeof(KeyT) + SYM_BYTES);
+    KeyT *s_key = reinterpret_cast<KeyT *>(mine);
+    uint8_t *s_sym = mine + size_t(kcap) * sizeof(KeyT);
+    uint32_t sym_addr = smem_addr(s_sym);
+    asm volatile("" : "+r"(sym_addr));
+    ts_lut_init(s_lut, lut);
+    __syncthreads();
+    // ---- which sequences ----
+    int64_t lo = 0, hi = 0;
+    if (!LONG) {
+        if (lane == 0) {
+            const int64_t W = int64_t(gridDim.x) * CS_WARPS, w = int64_t(blockIdx.x) * CS_WARPS + grp;
+            const int64_t r0 = __ldg(off), span = __ldg(off + nseq) - r0;
+            lo = (w == 0) ? 0 : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * w) / W));
+            hi = (w + 1 == W) ? nseq : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * (w + 1)) / W));
+        }
+        lo = __shfl_sync(FULL, lo, 0);
+        hi = __shfl_sync(FULL, hi, 0);
+    } else {
+        lo = blockIdx.x;
+        hi = int64_t(*n_long);
+    }
+    const uint32_t uk = uint32_t(k);
+    for (int64_t it = lo; it < hi; it += (LONG ? int64_t(gridDim.x) : 1)) {
+        const int64_t s = LONG ? long_list[it] : it;
+        const int64_t b = __ldg(off + s), e = __ldg(off + s + 1);
+        const int64_t L = e - b;
+        const int n = (L >= k) ? int(L - (k - 1)) : 0;          // windows of the sequence
+        if (n == 0) { if (g == 0) rowcount[s + 1] = 0; continue; }
+        if (!LONG && n > kcap) {
+            if (g == 0) long_list[atomicAdd(n_long, 1ull)] = s;
+            continue;
+        }
+        KeyT *keys = (LONG && n > kcap) ? gscratch + int64_t(blockIdx.x) * gscratch_stride : s_key;
+        // ---- scan: key of the window ending at residue b + (k-1) + i goes to keys[i] ----
+        bool first = true;
+        uint32_t tail0 = 0, tail1 = 0;
+        for (int64_t a = b; a < e;) {
+            const int64_t a2 = min(e, (a + SEG) & ~int64_t(15));
+            if (!first) {
+                if (g < k - 1) s_sym[TS_PAD - (k - 1) + g] = uint8_t(tail0);
+                if (g + 32 < k - 1) s_sym[TS_PAD - (k - 1) + g + 32] = uint8_t(tail1);
+            }
+            const int64_t base = a & ~int64_t(15);
+            const int lo_i = TS_PAD + int(a - base), hi_i = lo_i + int(a2 - a);
+            const int nvec = int((a2 - base + 15) >> 4);
+            if (g < nvec) {
+                const int64_t p = base + 16 * int64_t(g);
+                uint4 x;
+                if (p + 16 <= nres) {
+                    x = __ldg(reinterpret_cast<const uint4 *>(res + p));
+                } else {
+                    uint32_t w4[4] = {0, 0, 0, 0};
+                    for (int j = 0; j < 16; ++j)
+                        if (p + j < nres) w4[j >> 2] |= uint32_t(res[p + j]) << (8 * (j & 3));
+                    x = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                x.x = ts_translate4(x.x, s_lut);
+                x.y = ts_translate4(x.y, s_lut);
+                x.z = ts_translate4(x.z, s_lut);
+                x.w = ts_translate4(x.w, s_lut);
+                reinterpret_cast<uint4 *>(s_sym + TS_PAD)[g] = x;
+            }
+            gsync<GT>();
+            if (first) {
+                for (int i = g; i < lo_i; i += GT) s_sym[i] = uint8_t(SYM_BAD);
+                gsync<GT>();
+            }
+            const int nn = hi_i - lo_i;
+            const int C = ((((nn + GT - 1) / GT) + 3) >> 2 | 1) << 2;       // smallest 4 * odd >= ceil(nn / GT)
+            const int i0 = lo_i + g * C, i1 = min(i0 + C, hi_i);
+            if (i0 < i1) {
+                uint32_t run = 0;
+                KeyT code = 0;
+                uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
+                for (uint32_t j = 1; j < uk; ++j, ++p) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + KeyT(sy);
+                }
+                const uint32_t pend = sym_addr + uint32_t(i1);
+                const uint32_t back = uk - 1u;
+                // index of the window ending at symbol p: (a - b) + (p - sym_addr - lo_i) - (k - 1)
+                int64_t widx = (a - b) + int64_t(i0 - lo_i) - int64_t(k - 1);
+#pragma unroll 2
+                for (; p < pend; ++p, ++widx) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + KeyT(sy);
+                    if (widx >= 0) {
+                        KeyT key = NONE;
+                        if (run >= uk) {
+                            if (MODE == 1) { const int32_t c = __ldg(col_of_code + code); if (c >= 0) key = KeyT(c); }
+                            else key = code;
+                        }
+                        keys[widx] = key;
+                    }
+                    code -= KeyT(lds_u8<0>(p - back)) * pow_k1;
+                }
+            }
+            gsync<GT>();
+            if (g < k - 1) tail0 = s_sym[hi_i - (k - 1) + g];
+            if (g + 32 < k - 1) tail1 = s_sym[hi_i - (k - 1) + g + 32];
+            gsync<GT>();
+            first = false;
+            a = a2;
+        }
+        // ---- sort ----
+        group_sort<KeyT, GT>(keys, n, g);
+        // ---- encode: run heads -> tmp[b + slot] ----
+        int total = 0;
+        for (int p0 = 0; p0 < n; p0 += GT) {
+            const int p = p0 + g;
+            KeyT key = NONE;
+            bool head = false;
+            int32_t col = -1;
+            int len = 0;
+            if (p < n) {
+                key = keys[p];
+                head = key != NONE && (p == 0 || keys[p - 1] != key);
+                if (head && MODE == 2 && sb.codes) { col = sorted_lookup(sb, uint64_t(key)); head = col >= 0; }
+                if (head) {
+                    int q = p + 1;
+                    while (q < n && keys[q] == key) ++q;
+                    len = q - p;
+                }
+            }
+            const unsigned m = __ballot_sync(FULL, head);
+            int slot = total + __popc(m & ((1u << lane) - 1u));
+            int round = __popc(m);
+            if (LONG) {
+                if (lane == 0) s_wcnt[threadIdx.x >> 5] = round;
+                __syncthreads();
+                int before = 0, all = 0;
+#pragma unroll
+                for (int w = 0; w < CS_LONG_THREADS / 32; ++w) {
+                    const int c = s_wcnt[w];
+                    if (w < int(threadIdx.x >> 5)) before += c;
+                    all += c;
+                }
+                slot += before;
+                round = all;
+                __syncthreads();
+            }
+            if (head) {
+                tmp_keys[b + slot] = key;
+                if (MODE == 2 && tmp_cols) tmp_cols[b + slot] = col;
+                tmp_vals[b + slot] = len;
+            }
+            total += round;
+        }
+        if (g == 0) rowcount[s + 1] = total;
+        gsync<GT>();                        // the key buffer is rewritten by the next sequence
+    }
+}
+
+// out[rowptr[s] + j] = tmp[off[s] + j] for j < rowptr[s+1] - rowptr[s]; one warp per row
+template <typename KeyT>
+__global__ void __launch_bounds__(256) csr_compact_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ rowptr, int64_t nseq,
+                                                          const KeyT *__restrict__ tmp_keys, const int32_t *__restrict__ tmp_cols,
+                                                          const int32_t *__restrict__ tmp_vals, KeyT *__restrict__ keys_out,
+                                                          uint32_t *__restrict__ cols_out, int32_t *__restrict__ vals_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nseq; s += nwarps) {
+        const int64_t src = __ldg(off + s), dst = rowptr[s], cnt = rowptr[s + 1] - dst;
+        for (int64_t j = lane; j < cnt; j += 32) {
+            if (keys_out) keys_out[dst + j] = tmp_keys[src + j];
+            if (cols_out) cols_out[dst + j] = uint32_t(tmp_cols[src + j]);
+            vals_out[dst + j] = tmp_vals[src + j];
+        }
+    }
+}
+
+// bucket[q] = first index whose code >> shift is >= q  (q in [0, nbucket]); codes ascending
+__global__ void __launch_bounds__(256) bucket_index_kernel(const uint64_t *__restrict__ codes, int64_t K, int shift, int64_t nbucket,
+                                                           uint32_t *__restrict__ bucket) {
+    for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q <= nbucket; q += int64_t(gridDim.x) * blockDim.x) {
+        int64_t lo = 0, hi = K;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((codes[mid] >> shift) < uint64_t(q)) lo = mid + 1; else hi = mid;
+        }
+        bucket[q] = uint32_t(lo);
+    }
+}
+
+static size_t cal(size_t x) { return (x + 255) & ~size_t(255); }
+constexpr int64_t CS_MAX_RES = 1ll << 30;
+constexpr int CS_BUCKET_BITS = 20;
+
+static int cs_bits_for(unsigned __int128 n) { int b = 1; while (b < 64 && (((unsigned __int128)1) << b) < n) ++b; return b; }
+
+struct CsPlan {
+    size_t key_bytes;
+    int long_grid;
+    int64_t gscratch_stride;     // keys per CTA of the long kernel's global scratch (0: none needed)
+    size_t tmp_keys, tmp_cols, tmp_vals, rowcount, long_list, n_long, gscratch, bucket, scan_temp;
+    size_t total;
+};
+
+static CsPlan cs_plan(int64_t nres, int64_t nseq, int64_t max_len, size_t key_bytes, bool with_cols, bool with_bucket) {
+    CsPlan p{};
+    p.key_bytes = key_bytes;
+    p.long_grid = sm_count() * 2;
+    p.gscratch_stride = (max_len > CS_KCAP_C) ? ((max_len + 31) & ~int64_t(31)) : 0;
+    size_t t_scan = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, t_scan, (const int64_t *)nullptr, (int64_t *)nullptr, nseq + 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += cal(bytes); return at; };
+    p.tmp_keys = take(size_t(nres) * key_bytes);
+    p.tmp_cols = take(with_cols ? size_t(nres) * 4 : 0);
+    p.tmp_vals = take(size_t(nres) * 4);
+    p.rowcount = take(size_t(nseq + 1) * 8);
+    p.long_list = take(size_t(nseq) * 8);
+    p.n_long = take(8);
+    p.gscratch = take(size_t(p.gscratch_stride) * key_bytes * p.long_grid);
+    p.bucket = take(with_bucket ? ((size_t(1) << CS_BUCKET_BITS) + 2) * 4 : 0);
+    p.scan_temp = take(t_scan);
+    p.total = o + 512;
+    return p;
+}
+
+template <typename KeyT, int MODE>
+static int cs_run(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                  const int32_t *d_col_of_code, SortedBasis sb, int64_t max_len, const CsPlan &pl, char *ws, int64_t *d_rowptr,
+                  KeyT *d_keys_out, uint32_t *d_cols_out, int32_t *d_vals, cudaStream_t st) {
+    KeyT pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= KeyT(nsym);
+    KeyT *tmp_keys = reinterpret_cast<KeyT *>(ws + pl.tmp_keys);
+    int32_t *tmp_cols = (MODE == 2 && d_cols_out) ? reinterpret_cast<int32_t *>(ws + pl.tmp_cols) : nullptr;
+    int32_t *tmp_vals = reinterpret_cast<int32_t *>(ws + pl.tmp_vals);
+    int64_t *rowcount = reinterpret_cast<int64_t *>(ws + pl.rowcount);
+    int64_t *long_list = reinterpret_cast<int64_t *>(ws + pl.long_list);
+    unsigned long long *n_long = reinterpret_cast<unsigned long long *>(ws + pl.n_long);
+    KeyT *gscratch = pl.gscratch_stride ? reinterpret_cast<KeyT *>(ws + pl.gscratch) : nullptr;
+    SKM_CUDA_TRY(cudaMemsetAsync(n_long, 0, 8, st));
+    SKM_CUDA_TRY(cudaMemsetAsync(rowcount, 0, 8, st));
+    // warp kernel
+    {
+        constexpr int SYM_W = ts_sym_bytes(32 * CS_C);
+        const size_t smem = size_t(CS_WARPS) * (size_t(CS_KCAP_W) * sizeof(KeyT) + SYM_W);
+        auto kern = csr_sort_kernel<KeyT, MODE, false>;
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = int((227 * 1024) / (smem + 1536));
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        const int grid = (int)std::min<int64_t>((nseq + CS_WARPS - 1) / CS_WARPS, int64_t(sm_count()) * per_sm);
+        kern<<<grid, 32 * CS_WARPS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, sb, CS_KCAP_W,
+                                                 long_list, n_long, nullptr, 0, tmp_keys, tmp_cols, tmp_vals, rowcount);
+        SKM_LAUNCH_CHECK("csr_sort_kernel(warp)");
+    }
+    // long sequences (the list may be empty: the CTAs then exit at once)
+    if (max_len - (k - 1) > CS_KCAP_W) {
+        constexpr int SYM_C = ts_sym_bytes(CS_LONG_THREADS * CS_C);
+        const size_t smem = size_t(CS_KCAP_C) * sizeof(KeyT) + SYM_C;
+        auto kern = csr_sort_kernel<KeyT, MODE, true>;
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<pl.long_grid, CS_LONG_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, sb, CS_KCAP_C,
+                                                           long_list, n_long, gscratch, pl.gscratch_stride, tmp_keys, tmp_cols, tmp_vals, rowcount);
+        SKM_LAUNCH_CHECK("csr_sort_kernel(long)");
+    }
+    size_t temp_bytes = pl.total - pl.scan_temp;
+    SKM_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + pl.scan_temp, temp_bytes, rowcount, d_rowptr, nseq + 1, st));
+    csr_compact_kernel<KeyT><<<sm_count() * 8, 256, 0, st>>>(d_offsets, d_rowptr, nseq, tmp_keys, tmp_cols, tmp_vals, d_keys_out, d_cols_out, d_vals);
+    SKM_LAUNCH_CHECK("csr_compact_kernel");
+    return SKM_OK;
+}
+
+}  // namespace skm
+
+extern "C" {
+
+size_t skm_count_csr_sorted_workspace(int64_t nres, int64_t nseq, int64_t max_len, int key_bits) {
+    using namespace skm;
+    if (nres <= 0 || nseq <= 0) return 256;
+    return cs_plan(nres, nseq, max_len, key_bits == 64 ? 8 : 4, key_bits == 64, key_bits == 64).total + 256;
+}
+
+int skm_count_csr_sorted(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                         const uint8_t *d_lut, int nsym, int k, int key_bits, const int32_t *d_col_of_code, int64_t S,
+                         const uint64_t *d_sorted_codes, const int32_t *d_col_of_sorted, int64_t K, int64_t max_len,
+                         int64_t *d_rowptr, void *d_keys_out, uint32_t *d_cols_out, int32_t *d_vals, void *workspace,
+                         size_t workspace_bytes, skm_stream_t stream) {
+    using namespace skm;
+    int rc = check_common(d_residues, nres, d_offsets, nseq, d_lut, nsym, k);
+    if (rc) return rc;
+    if (key_bits != 32 && key_bits != 64) { set_error("skm_count_csr_sorted: key_bits must be 32 or 64"); return SKM_ERR_INVALID; }
+    if (!ts_supported(nsym, k)) { set_error("skm_count_csr_sorted: nsym=%d k=%d outside the kernel envelope", nsym, k); return SKM_ERR_UNSUPPORTED; }
+    unsigned __int128 S128;
+    code_space(nsym, k, &S128);
+    if (key_bits == 32 && S128 >= ((unsigned __int128)1 << 32)) { set_error("skm_count_csr_sorted: nsym^k needs 64-bit keys"); return SKM_ERR_INVALID; }
+    if (S128 > (((unsigned __int128)1 << 64) - 1)) { set_error("skm_count_csr_sorted: nsym^k = 2^64 collides with the invalid sentinel"); return SKM_ERR_UNSUPPORTED; }
+    if (d_col_of_code && (key_bits != 32 || (unsigned __int128)S != S128)) { set_error("skm_count_csr_sorted: a column table needs 32-bit keys and S = nsym^k"); return SKM_ERR_INVALID; }
+    if (d_sorted_codes && (key_bits != 64 || !d_col_of_sorted || K < 0)) { set_error("skm_count_csr_sorted: a sorted basis needs 64-bit keys and its column map"); return SKM_ERR_INVALID; }
+    if (d_cols_out && !d_sorted_codes) { set_error("skm_count_csr_sorted: d_cols_out needs a sorted basis"); return SKM_ERR_INVALID; }
+    if (!d_rowptr) { set_error("skm_count_csr_sorted: d_rowptr is NULL"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_rowptr, 0, 8 * (size_t)(nseq + 1), st));
+    if (nseq == 0 || nres == 0) return SKM_OK;
+    if (!d_vals || (!d_keys_out && !d_cols_out)) { set_error("skm_count_csr_sorted: NULL output"); return SKM_ERR_INVALID; }
+    if (nres >= CS_MAX_RES || nseq >= (1ll << 31)) { set_error("skm_count_csr_sorted: more than 2^30 residues per call; split the shard"); return SKM_ERR_UNSUPPORTED; }
+    if (max_len <= 0 || max_len > nres) max_len = nres;          // unknown: assume the worst
+    const bool wide = key_bits == 64;
+    const bool with_bucket = wide && d_sorted_codes && K > 64;
+    const CsPlan pl = cs_plan(nres, nseq, max_len, wide ? 8 : 4, wide, wide);
+    if (!workspace || workspace_bytes < pl.total + 256) { set_error("skm_count_csr_sorted: workspace %zu < %zu", workspace_bytes, pl.total + 256); return SKM_ERR_WORKSPACE; }
+    char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    SortedBasis sb{d_sorted_codes, d_col_of_sorted, nullptr, K, 0};
+    if (with_bucket) {
+        const int bits = cs_bits_for(S128);
+        sb.shift = bits > CS_BUCKET_BITS ? bits - CS_BUCKET_BITS : 0;
+        const int64_t nbucket = int64_t((S128 - 1) >> sb.shift) + 1;            // <= 2^20
+        uint32_t *bucket = reinterpret_cast<uint32_t *>(ws + pl.bucket);
+        bucket_index_kernel<<<(int)std::min<int64_t>((nbucket + 256) / 256, 1024), 256, 0, st>>>(d_sorted_codes, K, sb.shift, nbucket, bucket);
+        SKM_LAUNCH_CHECK("bucket_index_kernel");
+        sb.bucket = bucket;
+    }
+    if (!wide) {
+        if (d_col_of_code) return cs_run<uint32_t, 1>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, sb, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
+        return cs_run<uint32_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
+    }
+    if (d_sorted_codes) return cs_run<uint64_t, 2>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint64_t *)d_keys_out, d_cols_out, d_vals, st);
+    return cs_run<uint64_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint64_t *)d_keys_out, nullptr, d_vals, st);
+}
+
+}  // extern "C"

@@ -399,19 +399,29 @@ def count_over_kmers(batch: SequenceBatch, alphabet, k: int, kmerlist: Sequence[
     return gather_columns(C, index)
 
 
-def count_csr(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis] = None):
-    """Per-sequence sorted (column, count) pairs as CSR: (rowptr int64 [N+1], cols int32 [nnz], vals int32 [nnz])."""
+def count_csr(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[Basis] = None, method: str = "warp"):
+    """Per-sequence sorted (column, count) pairs as CSR: (rowptr int64 [N+1], cols int32 [nnz], vals int32 [nnz]).
+    method "warp" (default): a warp sorts one sequence's keys in shared memory (skm_count_csr_sorted);
+    "segsort": window keys in HBM + cub::DeviceSegmentedSort (skm_count_csr, the first implementation, kept as a
+    cross-check)."""
     tab = alphabet_tables(alphabet, batch.device)
     S = code_space(tab.nsym, k)
     dev = batch.device
-    ws_bytes = lib().skm_count_csr_workspace(batch.nres, batch.n)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rowptr = torch.empty(batch.n + 1, dtype=torch.int64, device=dev)
     cols = torch.empty(max(batch.nres, 1), dtype=torch.int32, device=dev)
     vals = torch.empty(max(batch.nres, 1), dtype=torch.int32, device=dev)
-    check(lib().skm_count_csr(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
-                              int(k), None if basis is None else _ptr(basis.col_of_code), S, _ptr(rowptr), _ptr(cols),
-                              _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+    if method == "segsort":
+        ws_bytes = lib().skm_count_csr_workspace(batch.nres, batch.n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().skm_count_csr(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
+                                  int(k), None if basis is None else _ptr(basis.col_of_code), S, _ptr(rowptr), _ptr(cols),
+                                  _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+    else:
+        ws_bytes = lib().skm_count_csr_sorted_workspace(batch.nres, batch.n, batch.max_len, 32)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().skm_count_csr_sorted(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut), tab.nsym,
+                                         int(k), 32, None if basis is None else _ptr(basis.col_of_code), S, None, None, 0,
+                                         batch.max_len, _ptr(rowptr), _ptr(cols), None, _ptr(vals), _ptr(ws), ws_bytes, _stream()))
     nnz = int(rowptr[-1].item()) if batch.n else 0
     return rowptr, cols[:nnz].clone(), vals[:nnz].clone()
 
@@ -874,7 +884,7 @@ def codes_to_columns(codes: torch.Tensor, basis: WideBasis) -> torch.Tensor:
 
 
 def count_csr_wide(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Optional[WideBasis] = None,
-                   max_chunk_res: int = WIDE_MAX_CHUNK_RES):
+                   max_chunk_res: int = WIDE_MAX_CHUNK_RES, method: str = "warp"):
     """Per-sequence distinct k-mers and their counts for any nsym^k <= 2^64 - 1.
     Returns (rowptr int64 [N+1], codes int64 (uint64 pattern) [nnz], cols int32 [nnz] or None, vals int32 [nnz]);
     a row's entries are ordered by code; with a basis, entries outside it are dropped and cols holds columns."""
@@ -887,17 +897,26 @@ def count_csr_wide(batch: SequenceBatch, alphabet: AlphabetT, k: int, basis: Opt
     base_nnz = 0
     for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
         sub = batch if (lo == 0 and hi == batch.n) else _sub_batch(batch, lo, hi)
-        ws_bytes = lib().skm_count_csr_wide_workspace(sub.nres, sub.n)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         cap = max(sub.nres, 1)
         rowptr = torch.empty(sub.n + 1, dtype=torch.int64, device=dev)
         codes = torch.empty(cap, dtype=torch.int64, device=dev)
         cols = torch.empty(cap, dtype=torch.int32, device=dev) if basis is not None else None
         vals = torch.empty(cap, dtype=torch.int32, device=dev)
-        check(lib().skm_count_csr_wide(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k),
-                                       None if basis is None else _ptr(basis.sorted_codes),
-                                       None if basis is None else _ptr(basis.col_of_sorted), 0 if basis is None else basis.K,
-                                       _ptr(rowptr), _ptr(codes), _ptr(cols), _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+        b_codes = None if basis is None else _ptr(basis.sorted_codes)
+        b_cols = None if basis is None else _ptr(basis.col_of_sorted)
+        b_K = 0 if basis is None else basis.K
+        if method == "segsort":          # the first implementation (window keys in HBM + cub::DeviceSegmentedSort), a cross-check
+            ws_bytes = lib().skm_count_csr_wide_workspace(sub.nres, sub.n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib().skm_count_csr_wide(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k),
+                                           b_codes, b_cols, b_K, _ptr(rowptr), _ptr(codes), _ptr(cols), _ptr(vals), _ptr(ws), ws_bytes, _stream()))
+        else:                            # a warp sorts one sequence's keys in shared memory
+            max_len = int(np.diff(sub.offsets_host).max()) if sub.n else 0
+            ws_bytes = lib().skm_count_csr_sorted_workspace(sub.nres, sub.n, max_len, 64)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib().skm_count_csr_sorted(_ptr(sub.residues), sub.nres, _ptr(sub.offsets), sub.n, _ptr(tab.lut), tab.nsym, int(k), 64,
+                                             None, 0, b_codes, b_cols, b_K, max_len, _ptr(rowptr), _ptr(codes), _ptr(cols), _ptr(vals),
+                                             _ptr(ws), ws_bytes, _stream()))
         nnz = int(rowptr[-1].item()) if sub.n else 0
         rowptrs.append(rowptr[(1 if rowptrs else 0):] + base_nnz)
         codes_p.append(codes[:nnz].clone())
@@ -929,6 +948,56 @@ def build_basis_wide_distributed(batch: SequenceBatch, alphabet, k: int, min_fil
         codes, counts, first = D.allgather_tables(codes, counts, first)
         merged = False
     return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter)
+
+
+DENSE_ROW_MAX_K = 4096          # widest basis whose per-sequence counts are kept as dense rows by vectorize()
+
+
+@dataclass
+class Vectorized:
+    """Result of vectorize(): the basis and the per-sequence counts in the layout the basis size calls for."""
+    path: str                               # "dense" | "csr" | "wide"
+    basis: "Basis | WideBasis"
+    counts: Optional[torch.Tensor] = None   # dense: int32 [N, K]
+    rowptr: Optional[torch.Tensor] = None   # csr / wide: int64 [N+1]
+    cols: Optional[torch.Tensor] = None     #             int32 [nnz] basis column of every entry
+    vals: Optional[torch.Tensor] = None     #             int32 [nnz]
+    codes: Optional[torch.Tensor] = None    # wide only: int64 (uint64 pattern) [nnz]
+
+    @property
+    def K(self) -> int:
+        return self.basis.K
+
+    @property
+    def nnz(self) -> int:
+        return int(self.vals.numel()) if self.vals is not None else int((self.counts != 0).sum().item())
+
+
+def vectorize(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0,
+              dense_max_K: int = DENSE_ROW_MAX_K) -> Vectorized:
+    """Both passes of the vectorize rule (kmerize.smk:85-120) for ANY alphabet / k with nsym^k <= 2^64 - 1:
+    first-occurrence basis + per-sequence counts.  Code spaces up to 2^27 use the table kernels (dense rows while
+    the basis has at most `dense_max_K` columns, CSR beyond); larger ones the sort-based wide path."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    if S <= _native.SKM_DENSE_MAX_SPACE:
+        basis = build_basis(batch, alphabet, k, min_filter)
+        if basis.K <= dense_max_K:
+            return Vectorized("dense", basis, counts=count_dense(batch, alphabet, k, basis))
+        parts, base = [], 0
+        for lo, hi in _chunks_by_residues(batch.offsets_host, (1 << 30) - 16):
+            sub = batch if (lo == 0 and hi == batch.n) else _sub_batch(batch, lo, hi)
+            rp, c, v = count_csr(sub, alphabet, k, basis)
+            parts.append((rp[(1 if parts else 0):] + base, c, v))
+            base += int(v.numel())
+        if not parts:
+            z32 = torch.zeros(0, dtype=torch.int32, device=batch.device)
+            return Vectorized("csr", basis, rowptr=torch.zeros(1, dtype=torch.int64, device=batch.device), cols=z32, vals=z32.clone())
+        cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
+        return Vectorized("csr", basis, rowptr=cat([p[0] for p in parts]), cols=cat([p[1] for p in parts]), vals=cat([p[2] for p in parts]))
+    basis = build_basis_wide(batch, alphabet, k, min_filter)
+    rowptr, codes, cols, vals = count_csr_wide(batch, alphabet, k, basis)
+    return Vectorized("wide", basis, rowptr=rowptr, cols=cols, vals=vals, codes=codes)
 
 
 # ---------------------------------------------------------------------------

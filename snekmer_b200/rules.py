@@ -54,6 +54,24 @@ class VectorizeResult:
         """float64 0/1 presence matrix, as the rule stores it (kmerize.smk:112-120)."""
         return (self.counts > 0).to(torch.float64).cpu().numpy()
 
+    def write_sidecar(self, path: str, alphabet, k: int) -> None:
+        """Binary side-car (.skmv, sidecar.py) of this shard: COUNTS as CSR instead of the dense float64 presence
+        matrix; ``sidecar.export_npz`` turns it back into the rule's .npz."""
+        from . import alphabet as _alpha
+        from . import sidecar
+
+        name = _alpha.get_alphabet_name(alphabet)
+        symbols = _alpha.symbols(name)
+        codes, ok = E.encode_kmers([str(x) for x in self.kmerlist], symbols, k)
+        assert bool(ok.all()), "a k-mer of the basis does not belong to the alphabet"
+        nz = self.counts.nonzero()
+        rowptr = torch.zeros(self.counts.shape[0] + 1, dtype=torch.int64, device=self.counts.device)
+        if nz.numel():
+            rowptr[1:] = torch.cumsum(torch.bincount(nz[:, 0], minlength=self.counts.shape[0]), 0)
+        vals = self.counts[nz[:, 0], nz[:, 1]] if nz.numel() else self.counts.new_zeros(0)
+        sidecar.write_vectors(path, name, k, symbols, codes, self.ids, self.seqs, self.lengths, rowptr.cpu().numpy(),
+                              nz[:, 1].to(torch.int32).cpu().numpy(), vals.to(torch.int32).cpu().numpy())
+
 
 def _reduced_strings(batch: E.SequenceBatch, alphabet) -> List[str]:
     red = bytes(E.reduce_bytes(batch, alphabet).cpu().numpy()).decode("latin-1") if batch.nres else ""
@@ -84,14 +102,17 @@ def vectorize_packed(ids: Sequence[str], residues: np.ndarray, offsets: np.ndarr
     return VectorizeResult(kmerlist, list(ids), _reduced_strings(batch, alphabet), lengths, counts)
 
 
-def vectorize_rule(fasta: str, out_npz: str, out_kmerobj: Optional[str], alphabet, k: int, min_filter: int = 0,
-                   basis_file: Optional[str] = None) -> VectorizeResult:
+def vectorize_rule(fasta: str, out_npz: Optional[str], out_kmerobj: Optional[str], alphabet, k: int, min_filter: int = 0,
+                   basis_file: Optional[str] = None, out_sidecar: Optional[str] = None) -> VectorizeResult:
     kmer = KmerVec(alphabet=alphabet, k=k)
     ids, residues, offsets = skio.read_fasta_packed(fasta, pinned=True)      # native multithreaded parser
     kmerbasis = skio.read_kmers(basis_file) if (basis_file and os.path.exists(basis_file)) else None
     r = vectorize_packed(ids, residues, offsets, alphabet, k, 0 if kmerbasis is not None else min_filter, kmerbasis, pinned=True)
     kmer.set_kmer_set(r.kmerlist)
-    np.savez_compressed(out_npz, kmerlist=r.kmerlist, ids=r.ids, seqs=r.seqs, vecs=r.vecs(), lengths=r.lengths)
+    if out_npz:
+        np.savez_compressed(out_npz, kmerlist=r.kmerlist, ids=r.ids, seqs=r.seqs, vecs=r.vecs(), lengths=r.lengths)
+    if out_sidecar:
+        r.write_sidecar(out_sidecar, alphabet, k)
     if out_kmerobj:
         with open(out_kmerobj, "wb") as f:
             pickle.dump(kmer, f)

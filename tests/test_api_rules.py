@@ -136,8 +136,15 @@ def test_rules_reproduce_reference_files(name, tmp_path):
     for nb in ("synA", "synB"):
         npz = str(tmp_path / f"{nb}.npz")
         kobj = str(tmp_path / f"{nb}.kmers")
-        R.vectorize_rule(os.path.join(GOLDEN, f"{nb}.fasta"), npz, kobj, a, k, min_filter=mf)
+        side = str(tmp_path / f"{nb}.skmv")
+        R.vectorize_rule(os.path.join(GOLDEN, f"{nb}.fasta"), npz, kobj, a, k, min_filter=mf, out_sidecar=side)
         z = np.load(npz)
+        # the binary side-car exports back to the same .npz content
+        from snekmer_b200 import sidecar as SC
+        SC.export_npz(side, str(tmp_path / f"{nb}.side.npz"))
+        z2 = np.load(str(tmp_path / f"{nb}.side.npz"))
+        for key in ("kmerlist", "ids", "seqs", "vecs", "lengths"):
+            assert z2[key].dtype == z[key].dtype and np.array_equal(z2[key], z[key]), key
         assert sorted(z.files) == ["ids", "kmerlist", "lengths", "seqs", "vecs"]
         assert list(z["kmerlist"]) == list(d[f"{nb}_kmerlist"]) and z["kmerlist"].dtype == d[f"{nb}_kmerlist"].dtype
         assert list(z["ids"]) == list(d[f"{nb}_ids"])

@@ -162,3 +162,75 @@ def test_wide_sweep_properties_full_size():
     t2 = E.basis_table_local(sub2, a, k, int(offs[half]) & ~15)
     bb = E.basis_table_finalize(a, k, torch.cat([t1[0], t2[0]]), torch.cat([t1[1], t2[1]]), torch.cat([t1[2], t2[2]]), False, 0)
     assert torch.equal(bb.codes, b.codes) and torch.equal(bb.counts, b.counts)
+
+
+@pytest.mark.parametrize("a,k,path", [(5, 3, "dense"), (0, 14, "csr"), (2, 12, "csr"), (None, 7, "wide"), (None, 14, "wide")])
+def test_vectorize_dispatch_matches_oracle(a, k, path):
+    """engine.vectorize picks dense rows / table CSR / sort-based wide by code-space and basis size; all three
+    agree with the oracle's basis (order included) and per-sequence counts."""
+    rng = np.random.default_rng(k + 100)
+    seqs = _rand_seqs(rng, 400, 0, 500)
+    (si, pos, code, valid), _ = _oracle(seqs, a, k)
+    want_b, want_cnt = O.basis_codes(si, pos, code, valid, 0)
+    batch = E.SequenceBatch.from_strings(seqs)
+    v = E.vectorize(batch, a, k, dense_max_K=2048)
+    assert v.path == path and v.K == len(want_b)
+    assert np.array_equal(v.basis.codes_host(), want_b)
+    assert np.array_equal(v.basis.counts.cpu().numpy(), want_cnt)
+    dense = O.count_matrix(si, code, valid, len(seqs), want_b) if len(want_b) * len(seqs) < 5e7 else None
+    if v.path == "dense":
+        assert np.array_equal(v.counts.cpu().numpy(), dense)
+    else:
+        rp = v.rowptr.cpu().numpy()
+        rows = np.repeat(np.arange(len(seqs)), np.diff(rp))
+        cols, vals = v.cols.cpu().numpy().astype(np.int64), v.vals.cpu().numpy()
+        assert int(vals.sum()) == int(valid.sum())                 # min_filter 0: every valid window is counted
+        if dense is not None:
+            rebuilt = np.zeros_like(dense)
+            rebuilt[rows, cols] = vals
+            assert np.array_equal(rebuilt, dense)
+        else:
+            wr, wc, wv = O.count_csr(si, code, valid, len(seqs))
+            assert np.array_equal(rp, wr) and np.array_equal(np.sort(want_b[cols]), np.sort(wc)) and int(vals.sum()) == int(wv.sum())
+
+
+def _long_mix(rng):
+    """Sequences around every buffer boundary of the warp-sort CSR kernel: warp buffer 1024 windows, CTA buffer 8192,
+    global scratch beyond; plus low-complexity runs."""
+    aa = np.array(list("ACDEFGHIKLMNPQRSTVWYX"))
+    lens = [0, 1, 7, 8, 9, 1023, 1024, 1025, 1030, 1031, 1032, 1040, 3000, 8191, 8192, 8199, 8200, 8210, 20000, 33, 350, 350]
+    seqs = ["".join(rng.choice(aa, size=n)) for n in lens]
+    seqs += ["A" * 2500, "AC" * 700, "ACDEFGHIKL" * 1200, "X" * 50, "ACDX" * 300]
+    seqs += _rand_seqs(rng, 200, 0, 600)
+    return seqs
+
+
+@pytest.mark.parametrize("a,k", [(5, 3), (0, 8), (2, 8), (None, 5), (None, 8), (None, 14), (0, 40)])
+def test_warp_sort_csr_long_sequences_and_cross_check(a, k):
+    rng = np.random.default_rng(k + 7)
+    seqs = _long_mix(rng)
+    (si, pos, code, valid), _ = _oracle(seqs, a, k)
+    want = O.count_csr(si, code, valid, len(seqs))
+    batch = E.SequenceBatch.from_strings(seqs)
+    nsym = len(O.build_lut(a)[1])
+    if nsym ** k < 2 ** 32:
+        for method in ("warp", "segsort"):
+            rp, cols, vals = E.count_csr(batch, a, k, None, method=method)
+            assert np.array_equal(rp.cpu().numpy(), want[0]), method
+            assert np.array_equal(cols.cpu().numpy().view(np.uint32).astype(np.uint64), want[1]), method
+            assert np.array_equal(vals.cpu().numpy(), want[2]), method
+        if nsym ** k <= 2 ** 27:
+            tb = E.build_basis(batch, a, k, 1)
+            r1 = E.count_csr(batch, a, k, tb, method="warp")
+            r2 = E.count_csr(batch, a, k, tb, method="segsort")
+            assert all(torch.equal(x, y) for x, y in zip(r1, r2))
+    for method in ("warp", "segsort"):
+        rp, codes, _, vals = E.count_csr_wide(batch, a, k, None, method=method)
+        _check_csr((rp, codes, vals), want, len(seqs))
+    wb = E.build_basis_wide(batch, a, k, 1)
+    r1 = E.count_csr_wide(batch, a, k, wb, method="warp")
+    r2 = E.count_csr_wide(batch, a, k, wb, method="segsort")
+    assert all(torch.equal(x, y) for x, y in zip(r1, r2))
+    want_b, _ = O.basis_codes(si, pos, code, valid, 1)
+    _check_csr((r1[0], r1[1], r1[3]), O.count_csr(si, code, np.isin(code, want_b) & valid, len(seqs)), len(seqs))
+    assert np.array_equal(want_b[r1[2].cpu().numpy()], _u64(r1[1]))
