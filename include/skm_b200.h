@@ -87,7 +87,8 @@ SKM_API int skm_encode_windows(const uint8_t *d_residues, int64_t nres,
  * (S <= SKM_DENSE_MAX_SPACE): d_count[c] += occurrences (init 0),
  * d_first[c] = min(res_base + position of window start) (init all-ones).
  * res_base is the global residue position of d_residues[0] so that several
- * shards / GPUs can be merged by sum / min before skm_basis_finalize. */
+ * shards / GPUs can be merged by sum / min before skm_basis_finalize.
+ * d_first may be NULL: occurrence counts only (the Totals row of learn.smk:380). */
 SKM_API int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres,
                          const int64_t *d_offsets, int64_t nseq,
                          const uint8_t *d_lut, int nsym, int k,
@@ -169,6 +170,22 @@ SKM_API int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int6
                      int64_t *d_vals_out, int64_t *d_nnz, void *workspace,
                      size_t workspace_bytes, skm_stream_t stream);
 
+/* (a12 at large K, grouped) the same COO list built one annotation slice at a time with 32-bit keys.  The caller
+ * gathers the sequences of annotations [ann_lo, ann_lo + ann_n) into one batch (skm_gather_sequences; unannotated
+ * sequences never enter) with ann_n * nsym^k < 2^32 - 1; their (key, count) runs are appended at *d_nnz_inout
+ * (device int64, read and advanced in stream order) as global keys ann * S + code.  Slices processed in annotation
+ * order leave one sorted list.  Entries beyond out_capacity are dropped (check *d_nnz_inout <= capacity afterwards). */
+SKM_API size_t skm_learn_sparse_group_workspace(int64_t nres);
+SKM_API int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                           const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo,
+                           int64_t ann_n, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity,
+                           int64_t *d_nnz_inout, void *workspace, size_t workspace_bytes, skm_stream_t stream);
+/* d_out_residues[d_out_offsets[i] ...] = sequence d_sel[i] of (d_residues, d_offsets): reorders / selects
+ * sequences on the device (grouping by annotation, learn.smk:316-326 keeps only annotated sequences). */
+SKM_API int skm_gather_sequences(const uint8_t *d_residues, const int64_t *d_offsets, const int64_t *d_sel,
+                         int64_t n_sel, uint8_t *d_out_residues, const int64_t *d_out_offsets,
+                         skm_stream_t stream);
+
 /* Merge.merge_dataframes (learn.smk:467-494) for sparse matrices / fan-in of per-GPU lists:
  * entries with equal keys are summed; output sorted by key, capacity n, count in *d_n_out. */
 SKM_API size_t skm_coo_merge_workspace(int64_t n);
@@ -192,10 +209,13 @@ SKM_API int skm_basis_sorted_local(const uint8_t *d_residues, int64_t nres, cons
  * count > min_filter kept (kmerize.smk:97-104), ordered by first position.  d_basis_out / d_basis_counts_out
  * (nullable): codes and counts in first-occurrence order; d_sorted_codes_out + d_col_of_sorted_out: the kept
  * codes in ascending order with the basis column of each (the lookup structure of skm_count_csr_wide /
- * skm_codes_to_columns).  All outputs need capacity n; *d_K_out = basis size. */
+ * skm_codes_to_columns).  first_bound: an exclusive upper bound of the first positions (the total residue count
+ * of all shards; <= 0 = unknown) — it limits the bits of the ordering sort.  All outputs need capacity n;
+ * *d_K_out = basis size. */
 SKM_API size_t skm_basis_sorted_finalize_workspace(int64_t n);
 SKM_API int skm_basis_sorted_finalize(const uint64_t *d_codes, const int64_t *d_counts, const int64_t *d_first,
-                              int64_t n, int merged, int64_t min_filter, uint64_t *d_basis_out,
+                              int64_t n, int merged, int64_t min_filter, int64_t first_bound,
+                              uint64_t *d_basis_out,
                               int64_t *d_basis_counts_out, uint64_t *d_sorted_codes_out,
                               int32_t *d_col_of_sorted_out, int64_t *d_K_out, void *workspace,
                               size_t workspace_bytes, skm_stream_t stream);

@@ -56,12 +56,15 @@ SIGNATURES = {
     "skm_basis_sorted_local_workspace": (_sz, [_i64]),
     "skm_basis_sorted_local": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_basis_sorted_finalize_workspace": (_sz, [_i64]),
-    "skm_basis_sorted_finalize": (_int, [_p, _p, _p, _i64, _int, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "skm_basis_sorted_finalize": (_int, [_p, _p, _p, _i64, _int, _i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_codes_to_columns": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "skm_count_csr_wide_workspace": (_sz, [_i64, _i64]),
     "skm_count_csr_wide": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_count_csr_sorted_workspace": (_sz, [_i64, _i64, _i64, _int]),
     "skm_count_csr_sorted": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _int, _p, _i64, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "skm_learn_sparse_group_workspace": (_sz, [_i64]),
+    "skm_learn_sparse_group": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
+    "skm_gather_sequences": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "skm_coo_merge_workspace": (_sz, [_i64]),
     "skm_coo_merge": (_int, [_p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "skm_csc_build_workspace": (_sz, [_i64, _i64]),

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
                         atomicAdd(g_count + code, 1ull);
                         const unsigned long long pos = res_base + uint64_t(r_lo) + rel;
                         // stale reads can only be too large (first is monotone decreasing): never skips a needed min
-                        if (pos < __ldcg(g_first + code)) atomicMin(g_first + code, pos);
+                        if (g_first && pos < __ldcg(g_first + code)) atomicMin(g_first + code, pos);
                     }
                 }
             },
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
             const uint32_t c = s_cnt[i];
             if (c) {
                 atomicAdd(g_count + i, (unsigned long long)c);
-                atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + s_min[i]));
+                if (g_first) atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + s_min[i]));
             }
         }
     }
@@ -166,7 +166,7 @@ int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres, const int64_t 
         set_error("skm_basis_accumulate: code space %d^%d exceeds the table limit 2^27 (use the sorted path)", nsym, k);
         return SKM_ERR_UNSUPPORTED;
     }
-    if (!d_count || !d_first) { set_error("skm_basis_accumulate: NULL table"); return SKM_ERR_INVALID; }
+    if (!d_count) { set_error("skm_basis_accumulate: NULL table"); return SKM_ERR_INVALID; }     // d_first may be NULL: counts only
     if (nseq == 0 || nres == 0) return SKM_OK;
     if (!ts_supported(nsym, k)) { set_error("skm_basis_accumulate: nsym=%d k=%d outside the kernel envelope (nsym <= %d, k <= %d)", nsym, k, TS_MAX_NSYM, TS_MAX_K); return SKM_ERR_UNSUPPORTED; }
     const int64_t S = (int64_t)S128;

@@ -31,15 +31,17 @@ constexpr int SP_SYM_BYTES = ts_sym_bytes(SP_SEG);
 
 // keys[p] for every residue position p of [off[0], off[nseq]) (p = position of the window's LAST residue):
 //   MODE 0: column (col_of_code) or code, 32-bit, all-ones when invalid / filtered
-//   MODE 1: ann_id[row] * S + code, 64-bit, `invalid` (= n_ann * S, one past the largest key) when the window is
-//           invalid or the sequence is not annotated: the sort then only needs the bits of n_ann * S
+//   MODE 1: (ann_id[row] - ann_lo) * S + code, `invalid` (one past the largest key, or all-ones) when the window is
+//           invalid or the sequence's annotation is outside [ann_lo, ann_hi): the sort then only needs the bits of
+//           the largest key.  32-bit keys when (ann_hi - ann_lo) * S < 2^32 (skm_learn_sparse_group).
 template <int MODE, typename KeyT>
 __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *__restrict__ res, int64_t nres,
                                                                  const int64_t *__restrict__ off, int64_t nseq,
                                                                  const uint8_t *__restrict__ lut, uint32_t nsym, int k,
                                                                  uint32_t pow_k1, const int32_t *__restrict__ col_of_code,
                                                                  const int32_t *__restrict__ ann_id, uint64_t S,
-                                                                 KeyT invalid, KeyT *__restrict__ keys) {
+                                                                 KeyT invalid, KeyT *__restrict__ keys, int32_t ann_lo = 0,
+                                                                 int32_t ann_hi = 0x7FFFFFFF) {
     extern __shared__ __align__(128) uint8_t s_sym[];
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_ctl[4];
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *
                                              if (row != ann_row) {
                                                  ann_row = row;
                                                  const int32_t a = __ldg(ann_id + row);
-                                                 ann_base = (a >= 0) ? uint64_t(a) * S : ~0ull;
+                                                 ann_base = (a >= ann_lo && a < ann_hi) ? uint64_t(a - ann_lo) * S : ~0ull;
                                              }
                                              if (ann_base != ~0ull) key = KeyT(ann_base + code);
                                          }
@@ -364,6 +366,96 @@ int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int64_t *d_o
     SKM_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, keys_b, d_keys_out, d_vals_out, num_runs, (int)nres, st));
     coo_finish_kernel<<<1, 1, 0, st>>>(d_keys_out, num_runs, invalid, d_nnz);
     SKM_LAUNCH_CHECK("coo_finish_kernel");
+    return SKM_OK;
+}
+
+// ---- grouped variant: 32-bit keys over a slice of annotations --------------------------------------------
+// The caller has gathered the sequences of annotations [ann_lo, ann_lo + ann_n) into one contiguous batch
+// (skm_gather_sequences), with ann_n * S < 2^32: keys fit 32 bits, the radix sort moves half the bytes per pass and
+// needs only the bits of ann_n * S, and unannotated sequences never enter a sort.  The (key, count) runs are
+// appended to the output at *d_nnz_inout as 64-bit global keys (ann_lo * S + key); groups processed in annotation
+// order therefore leave one globally sorted COO list.
+size_t skm_learn_sparse_group_workspace(int64_t nres) {
+    using namespace skm;
+    if (nres <= 0) return 256;
+    size_t t_sort = 0, t_rle = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t_sort, (const uint32_t *)nullptr, (uint32_t *)nullptr, nres, 0, 32);
+    cub::DeviceRunLengthEncode::Encode(nullptr, t_rle, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int32_t *)nullptr,
+                                       (int64_t *)nullptr, (int)std::min<int64_t>(nres, (1ll << 31) - 1));
+    return 4 * al(size_t(nres) * 4) + al(std::max(t_sort, t_rle)) + 1024;
+}
+
+namespace skm {
+// out[base + i] = (key_base + uniq[i], counts[i]) for the runs below the invalid key; base = *nnz
+__global__ void __launch_bounds__(256) coo_append_kernel(const uint32_t *__restrict__ uniq, const int32_t *__restrict__ counts,
+                                                         const int64_t *__restrict__ num_runs, uint32_t invalid, uint64_t key_base,
+                                                         const int64_t *__restrict__ nnz, int64_t capacity,
+                                                         uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out,
+                                                         int64_t *__restrict__ n_new) {
+    int64_t n = *num_runs;
+    while (n > 0 && uniq[n - 1] >= invalid) --n;            // at most two trailing runs (invalid key, all-ones fill)
+    const int64_t base = *nnz;
+    if (base + n > capacity) n = capacity > base ? capacity - base : 0;      // the host checks the total afterwards
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        keys_out[base + i] = key_base + uniq[i];
+        vals_out[base + i] = counts[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_new = n;
+}
+__global__ void add_i64_kernel(int64_t *dst, const int64_t *src) { *dst += *src; }
+}  // namespace skm
+
+int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                           const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo, int64_t ann_n,
+                           uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity, int64_t *d_nnz_inout,
+                           void *workspace, size_t workspace_bytes, skm_stream_t stream) {
+    using namespace skm;
+    int rc = check_common(d_residues, nres, d_offsets, nseq, d_lut, nsym, k);
+    if (rc) return rc;
+    if (!ts_supported(nsym, k)) { set_error("skm_learn_sparse_group: nsym=%d k=%d outside the kernel envelope", nsym, k); return SKM_ERR_UNSUPPORTED; }
+    unsigned __int128 S128;
+    code_space(nsym, k, &S128);
+    if (ann_lo < 0 || ann_n < 1 || ann_lo + ann_n > 0x7FFFFFFF || (unsigned __int128)ann_n * S128 >= (((unsigned __int128)1) << 32) - 1) {
+        set_error("skm_learn_sparse_group: ann_n * nsym^k must stay below 2^32 - 1");
+        return SKM_ERR_UNSUPPORTED;
+    }
+    if (!d_nnz_inout || out_capacity < 0) { set_error("skm_learn_sparse_group: bad output arguments"); return SKM_ERR_INVALID; }
+    if (nseq == 0 || nres == 0) return SKM_OK;
+    if (nres >= (1ll << 31)) { set_error("skm_learn_sparse_group: more than 2^31 residues per call; split the group"); return SKM_ERR_UNSUPPORTED; }
+    if (!d_ann_id || !d_keys_out || !d_vals_out) { set_error("skm_learn_sparse_group: NULL argument"); return SKM_ERR_INVALID; }
+    const size_t need = skm_learn_sparse_group_workspace(nres);
+    if (!workspace || workspace_bytes < need) { set_error("skm_learn_sparse_group: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const size_t seg = al(size_t(nres) * 4);
+    uint32_t *keys_a = (uint32_t *)p, *keys_b = (uint32_t *)(p + seg), *uniq = (uint32_t *)(p + 2 * seg);
+    int32_t *counts = (int32_t *)(p + 3 * seg);
+    void *temp = p + 4 * seg;
+    const size_t temp_cap = workspace_bytes - size_t((char *)temp - (char *)workspace);
+    size_t temp_bytes = temp_cap;
+    const uint64_t S = (uint64_t)S128;
+    const uint32_t invalid = uint32_t(uint64_t(ann_n) * S);
+    uint32_t pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
+    int64_t grid = int64_t(sm_count()) * 8;
+    const int64_t max_grid = (nres + SP_SEG - 1) / SP_SEG;
+    if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
+    SKM_CUDA_TRY(cudaMemsetAsync(keys_a, 0xFF, size_t(nres) * 4, st));       // positions outside every sequence
+    window_keys_kernel<1, uint32_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
+                                                                                      pow_k1, nullptr, d_ann_id, S, invalid, keys_a,
+                                                                                      (int32_t)ann_lo, (int32_t)(ann_lo + ann_n));
+    SKM_LAUNCH_CHECK("window_keys_kernel<1, u32>");
+    const int end_bit = std::min(32, bits_for((unsigned __int128)invalid + 1));
+    SKM_CUDA_TRY(cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, nres, 0, end_bit, st));
+    int64_t *num_runs = reinterpret_cast<int64_t *>(keys_a);                 // keys_a is free after the sort
+    int64_t *n_new = num_runs + 1;
+    temp_bytes = temp_cap;
+    SKM_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, keys_b, uniq, counts, num_runs, (int)nres, st));
+    const int g2 = (int)std::min<int64_t>((nres + 255) / 256, int64_t(sm_count()) * 8);
+    coo_append_kernel<<<g2, 256, 0, st>>>(uniq, counts, num_runs, invalid, uint64_t(ann_lo) * S, d_nnz_inout, out_capacity, d_keys_out, d_vals_out, n_new);
+    SKM_LAUNCH_CHECK("coo_append_kernel");
+    add_i64_kernel<<<1, 1, 0, st>>>(d_nnz_inout, n_new);
+    SKM_LAUNCH_CHECK("add_i64_kernel");
     return SKM_OK;
 }
 

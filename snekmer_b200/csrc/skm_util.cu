@@ -37,9 +37,45 @@ __global__ void __launch_bounds__(256) scatter_add_i64_kernel(const int64_t *__r
     }
 }
 
+// one warp per selected sequence: out_res[out_off[i] ...] = res[off[sel[i]] ...]
+__global__ void __launch_bounds__(256) gather_sequences_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ off,
+                                                               const int64_t *__restrict__ sel, int64_t n_sel,
+                                                               uint8_t *__restrict__ out_res, const int64_t *__restrict__ out_off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n_sel; i += nwarps) {
+        const int64_t s = __ldg(sel + i);
+        const int64_t b = __ldg(off + s), len = __ldg(off + s + 1) - b, d = __ldg(out_off + i);
+        // head bytes up to the first 4-byte boundary of the destination, then one word per lane and step
+        const int64_t head = min(len, (4 - (d & 3)) & 3);
+        if (lane < head) out_res[d + lane] = res[b + lane];
+        const int64_t words = (len - head) >> 2;
+        for (int64_t w = lane; w < words; w += 32) {
+            const uint8_t *src = res + b + head + 4 * w;
+            const uint32_t v = uint32_t(src[0]) | (uint32_t(src[1]) << 8) | (uint32_t(src[2]) << 16) | (uint32_t(src[3]) << 24);
+            *reinterpret_cast<uint32_t *>(out_res + d + head + 4 * w) = v;
+        }
+        const int64_t done = head + 4 * words;
+        if (lane < len - done) out_res[d + done + lane] = res[b + done + lane];
+    }
+}
+
 }  // namespace skm
 
 extern "C" {
+
+int skm_gather_sequences(const uint8_t *d_residues, const int64_t *d_offsets, const int64_t *d_sel, int64_t n_sel,
+                         uint8_t *d_out_residues, const int64_t *d_out_offsets, skm_stream_t stream) {
+    using namespace skm;
+    if (n_sel < 0) { set_error("skm_gather_sequences: negative size"); return SKM_ERR_INVALID; }
+    if (n_sel == 0) return SKM_OK;
+    if (!d_residues || !d_offsets || !d_sel || !d_out_residues || !d_out_offsets) { set_error("skm_gather_sequences: NULL argument"); return SKM_ERR_INVALID; }
+    const int grid = (int)std::min<int64_t>((n_sel + 7) / 8, int64_t(sm_count()) * 8);
+    gather_sequences_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_residues, d_offsets, d_sel, n_sel, d_out_residues, d_out_offsets);
+    SKM_LAUNCH_CHECK("gather_sequences_kernel");
+    return SKM_OK;
+}
 
 int skm_gather_columns(const void *d_in, int64_t rows, int64_t n, int elem_bytes, const int64_t *d_idx, int64_t p,
                        void *d_out, skm_stream_t stream) {

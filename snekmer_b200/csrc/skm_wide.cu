@@ -258,7 +258,7 @@ size_t skm_basis_sorted_finalize_workspace(int64_t n) {
 }
 
 int skm_basis_sorted_finalize(const uint64_t *d_codes, const int64_t *d_counts, const int64_t *d_first, int64_t n,
-                              int merged, int64_t min_filter, uint64_t *d_basis_out, int64_t *d_basis_counts_out,
+                              int merged, int64_t min_filter, int64_t first_bound, uint64_t *d_basis_out, int64_t *d_basis_counts_out,
                               uint64_t *d_sorted_codes_out, int32_t *d_col_of_sorted_out, int64_t *d_K_out,
                               void *workspace, size_t workspace_bytes, skm_stream_t stream) {
     using namespace skm;
@@ -320,7 +320,9 @@ int skm_basis_sorted_finalize(const uint64_t *d_codes, const int64_t *d_counts, 
     iota_u32_kernel<<<grid, 256, 0, st>>>(idx_a, n);
     SKM_LAUNCH_CHECK("iota_u32_kernel");
     temp_bytes = temp_cap;
-    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, reinterpret_cast<const uint64_t *>(first_sel), keys_b, idx_a, idx_b, n, 0, 64, st));
+    // positions are < first_bound <= 2^end_bit - 1 = the low bits of the padding value, which therefore still sorts last
+    const int order_bits = first_bound > 0 ? wbits_for((unsigned __int128)first_bound + 1) : 64;
+    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, reinterpret_cast<const uint64_t *>(first_sel), keys_b, idx_a, idx_b, n, 0, order_bits, st));
     basis_emit_kernel<<<grid, 256, 0, st>>>(d_sorted_codes_out, cnt_sel, idx_b, d_K_out, d_basis_out, d_basis_counts_out, d_col_of_sorted_out);
     SKM_LAUNCH_CHECK("basis_emit_kernel");
     return SKM_OK;

@@ -246,11 +246,24 @@ def basis_tables(S: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     return count, first
 
 
-def basis_accumulate(batch: SequenceBatch, alphabet: AlphabetT, k: int, count: torch.Tensor, first: torch.Tensor,
+def basis_accumulate(batch: SequenceBatch, alphabet: AlphabetT, k: int, count: torch.Tensor, first: Optional[torch.Tensor],
                      res_base: int = 0) -> None:
+    """count[c] += occurrences of code c; first[c] = min(first[c], global position) unless first is None
+    (occurrence counts only: the Totals row of learn.smk:380)."""
     tab = alphabet_tables(alphabet, batch.device)
     check(lib().skm_basis_accumulate(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), batch.n, _ptr(tab.lut),
                                      tab.nsym, int(k), int(res_base), _ptr(count), _ptr(first), _stream()))
+
+
+def kmer_totals(batch: SequenceBatch, alphabet: AlphabetT, k: int) -> torch.Tensor:
+    """int64 [nsym^k]: occurrences of every k-mer code over ALL sequences of the batch (learn.smk:380 Totals)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    count = torch.zeros(S, dtype=torch.int64, device=batch.device)
+    basis_accumulate(batch, alphabet, k, count, None, 0)
+    return count
 
 
 def basis_finalize(alphabet: AlphabetT, k: int, count: torch.Tensor, first: torch.Tensor, min_filter: int = 0) -> Basis:
@@ -655,15 +668,70 @@ def coo_merge(keys: torch.Tensor, vals: torch.Tensor) -> Tuple[torch.Tensor, tor
     return ok[:m].clone(), ov[:m].clone()
 
 
+def gather_sequences(batch: SequenceBatch, sel: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sequences sel[0], sel[1], ... of a batch packed back to back: (residues uint8 [R' + 16], offsets int64 [n_sel + 1])."""
+    dev = batch.device
+    sel = sel.to(device=dev, dtype=torch.int64).contiguous()
+    lens = (batch.offsets[1:] - batch.offsets[:-1])[sel]
+    out_off = torch.zeros(sel.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=out_off[1:])
+    total = int(out_off[-1].item()) if sel.numel() else 0
+    out_res = torch.empty(total + 32, dtype=torch.uint8, device=dev)
+    check(lib().skm_gather_sequences(_ptr(batch.residues), _ptr(batch.offsets), _ptr(sel), sel.numel(), _ptr(out_res), _ptr(out_off), _stream()))
+    return out_res, out_off
+
+
 def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int,
-                 max_chunk_res: int = 1 << 28) -> Tuple[torch.Tensor, torch.Tensor]:
+                 max_chunk_res: int = 1 << 28, method: str = "grouped") -> Tuple[torch.Tensor, torch.Tensor]:
     """Annotation x k-mer count matrix as a COO list sorted by key = ann * S + code
     (keys int64 holding the uint64 pattern, vals int64).  Sequences with ann_id < 0 do not
-    contribute (Totals come from the basis tables)."""
+    contribute (Totals come from the basis tables).
+
+    method "grouped" (default): the annotated sequences are gathered in annotation order and sorted one annotation
+    slice at a time with 32-bit keys (skm_learn_sparse_group); "global": one 64-bit radix sort over all window keys of
+    the shard (skm_learn_sparse, the first implementation, kept as a cross-check and for slices whose keys need more
+    than 32 bits)."""
     tab = alphabet_tables(alphabet, batch.device)
     dev = batch.device
     ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
     assert ann_id.numel() == batch.n
+    S = code_space(tab.nsym, k)
+    per_group = ((1 << 32) - 2) // S
+    if method == "grouped" and per_group >= 1 and batch.n > 0 and n_ann > 0:
+        key = torch.where((ann_id >= 0) & (ann_id < n_ann), ann_id, torch.full_like(ann_id, n_ann))
+        sk, order = torch.sort(key, stable=True)
+        starts = list(range(0, n_ann, per_group)) + [n_ann]
+        bounds = torch.searchsorted(sk, torch.tensor(starts, dtype=torch.int32, device=dev)).tolist()     # one sync
+        n_sel = bounds[-1]
+        if n_sel == 0:
+            z = torch.zeros(0, dtype=torch.int64, device=dev)
+            return z, z.clone()
+        g_res, g_off = gather_sequences(batch, order[:n_sel])
+        g_ann = sk[:n_sel].contiguous()
+        edge = g_off[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
+        if max(edge[i + 1] - (edge[i] & ~15) for i in range(len(starts) - 1)) < (1 << 31) - 64:
+            total = edge[-1]
+            keys = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+            vals = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+            dn = torch.zeros(1, dtype=torch.int64, device=dev)
+            ws = None
+            for gi in range(len(starts) - 1):
+                s0, s1 = bounds[gi], bounds[gi + 1]
+                if s1 == s0:
+                    continue
+                base = edge[gi] & ~15
+                nres = edge[gi + 1] - base
+                ws_bytes = lib().skm_learn_sparse_group_workspace(nres)
+                if ws is None or ws.numel() < ws_bytes:
+                    ws = None
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                offs = (g_off[s0:s1 + 1] - base).contiguous()
+                check(lib().skm_learn_sparse_group(_ptr(g_res[base:]), nres, _ptr(offs), s1 - s0, _ptr(tab.lut), tab.nsym, int(k),
+                                                   _ptr(g_ann[s0:s1]), starts[gi], starts[gi + 1] - starts[gi], _ptr(keys), _ptr(vals),
+                                                   total, _ptr(dn), _ptr(ws), ws.numel(), _stream()))
+            m = int(dn.item())
+            assert m <= total
+            return keys[:m].clone(), vals[:m].clone()
     parts_k, parts_v = [], []
     for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
         sub = _sub_batch(batch, lo, hi)
@@ -836,8 +904,9 @@ def basis_table_local(batch: SequenceBatch, alphabet: AlphabetT, k: int, res_bas
 
 
 def basis_table_finalize(alphabet: AlphabetT, k: int, codes: torch.Tensor, counts: torch.Tensor, first: torch.Tensor,
-                         merged: bool, min_filter: int = 0) -> WideBasis:
-    """Tables of one or more shards -> the basis in the reference's order (kmerize.smk:89-104)."""
+                         merged: bool, min_filter: int = 0, first_bound: int = 0) -> WideBasis:
+    """Tables of one or more shards -> the basis in the reference's order (kmerize.smk:89-104).
+    first_bound: exclusive upper bound of the first positions (total residues of all shards), 0 = unknown."""
     dev = _require_cuda(codes.device)
     tab = alphabet_tables(alphabet, dev)
     n = codes.numel()
@@ -850,7 +919,7 @@ def basis_table_finalize(alphabet: AlphabetT, k: int, codes: torch.Tensor, count
     scodes = torch.empty(cap, dtype=torch.int64, device=dev)
     scol = torch.empty(cap, dtype=torch.int32, device=dev)
     dK = torch.zeros(1, dtype=torch.int64, device=dev)
-    check(lib().skm_basis_sorted_finalize(_ptr(codes), _ptr(counts), _ptr(first), n, 1 if merged else 0, int(min_filter),
+    check(lib().skm_basis_sorted_finalize(_ptr(codes), _ptr(counts), _ptr(first), n, 1 if merged else 0, int(min_filter), int(first_bound),
                                           _ptr(basis), _ptr(bcnt), _ptr(scodes), _ptr(scol), _ptr(dK), _ptr(ws), ws_bytes, _stream()))
     K = int(dK.item())
     return WideBasis(tab.name, int(k), tab.symbols, basis[:K].clone(), bcnt[:K].clone(), scodes[:K].clone(), scol[:K].clone(), K)
@@ -859,7 +928,7 @@ def basis_table_finalize(alphabet: AlphabetT, k: int, codes: torch.Tensor, count
 def build_basis_wide(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0) -> WideBasis:
     """Pass 1 of the vectorize rule (kmerize.smk:89-104) for any nsym^k <= 2^64 - 1: sort-based."""
     codes, counts, first, merged = basis_table_local(batch, alphabet, k, 0)
-    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter)
+    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter, first_bound=batch.nres + 16)
 
 
 def wide_basis_from_codes(codes: np.ndarray, alphabet: AlphabetT, k: int, device=None) -> WideBasis:
@@ -940,14 +1009,15 @@ def build_basis_wide_distributed(batch: SequenceBatch, alphabet, k: int, min_fil
     global first positions, all_gather of the tables, one finalisation (sort by code, sum / min, order)."""
     from . import dist as D
 
+    total = 0
     if res_base is None:
-        res_base, _ = D.exclusive_prefix(batch.nres, batch.device)
+        res_base, total = D.exclusive_prefix(batch.nres, batch.device)
     codes, counts, first, merged = basis_table_local(batch, alphabet, k, res_base)
     _, w = D.world()
     if w > 1:
         codes, counts, first = D.allgather_tables(codes, counts, first)
         merged = False
-    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter)
+    return basis_table_finalize(alphabet, k, codes, counts, first, merged, min_filter, first_bound=(total + 16 * w) if total else 0)
 
 
 DENSE_ROW_MAX_K = 4096          # widest basis whose per-sequence counts are kept as dense rows by vectorize()

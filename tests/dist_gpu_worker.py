@@ -46,6 +46,22 @@ def main():
     np.add.at(want_M, np.where(ann < 0, n_ann, ann), C)
     assert np.array_equal(M.cpu().numpy(), want_M), "distributed learn"
     assert np.array_equal(totals.cpu().numpy(), C.sum(axis=0)), "distributed totals"
+    # sparse learn: grouped 32-bit-key build on the local shard + all_to_all of COO runs by annotation range
+    S = len(syms) ** k
+    keys, vals = E.learn_sparse(batch, a, k, torch.from_numpy(ann[lo:hi]), n_ann)
+    keys, vals = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
+    a_lo, a_hi = n_ann * rank // world, n_ann * (rank + 1) // world
+    full = np.zeros((n_ann, S), dtype=np.int64)
+    full[:, want_basis.astype(np.int64)] = want_M[:n_ann]
+    kk = keys.cpu().numpy()
+    got = np.zeros((n_ann, S), dtype=np.int64)
+    got[kk // S, kk % S] = vals.cpu().numpy()
+    assert np.all(kk[1:] > kk[:-1]) and (kk // S >= a_lo).all() and (kk // S < a_hi).all(), "sparse learn exchange ranges"
+    if mf == 0:
+        assert np.array_equal(got[a_lo:a_hi], full[a_lo:a_hi]), "sparse learn exchange"
+    else:   # the dense matrix only holds basis columns (count > min_filter); compare on those
+        cols = want_basis.astype(np.int64)
+        assert np.array_equal(got[a_lo:a_hi][:, cols], want_M[a_lo:a_hi]), "sparse learn exchange"
     # apply, annotation-sharded: all queries everywhere, my slice of annotation rows
     qbatch = E.SequenceBatch.from_strings(seqs[:500])
     Q = E.count_dense(qbatch, a, k, basis)

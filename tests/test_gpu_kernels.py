@@ -281,6 +281,33 @@ def test_learn_sparse_matches_dense(a, k, chunk):
     # merging a list with itself doubles every count
     k2, v2 = E.coo_merge(torch.cat([keys, keys]), torch.cat([vals, vals]))
     assert torch.equal(k2, keys) and torch.equal(v2, 2 * vals)
+    # the grouped 32-bit-key build (default) and the global 64-bit sort give the same list
+    kg, vg = E.learn_sparse(batch, a, k, torch.from_numpy(ann), n_ann, max_chunk_res=chunk, method="global")
+    assert torch.equal(kg, keys) and torch.equal(vg, vals)
+
+
+def test_learn_sparse_grouped_many_slices():
+    """C3 shape in small: 6-letter alphabet, k = 8 (S = 1,679,616 -> 2,556 annotations per 32-bit slice), 6,000
+    annotations -> 3 slices, some annotations empty, 30 % unannotated; equal to the global sort."""
+    from snekmer_b200 import alphabet as A
+
+    A.register_alphabet("syn6", {"AGILMV": "A", "FWY": "F", "NQSTC": "N", "DE": "D", "KRH": "K", "P": "P"})
+    rng = np.random.default_rng(8)
+    seqs = _rand_seqs(rng, 5000, 0, 200)
+    batch = E.SequenceBatch.from_strings(seqs)
+    n_ann = 6000
+    w = 1.0 / np.arange(1, n_ann + 1) ** 1.1
+    ann = rng.choice(n_ann, size=len(seqs), p=w / w.sum()).astype(np.int32)
+    ann[rng.random(len(seqs)) < 0.3] = -1
+    k1, v1 = E.learn_sparse(batch, "syn6", 8, torch.from_numpy(ann), n_ann)
+    k2, v2 = E.learn_sparse(batch, "syn6", 8, torch.from_numpy(ann), n_ann, method="global")
+    assert k1.numel() > 0 and torch.equal(k1, k2) and torch.equal(v1, v2)
+    # gather_sequences on its own
+    sel = torch.from_numpy(rng.permutation(len(seqs))[:777].astype(np.int64))
+    g_res, g_off = E.gather_sequences(batch, sel)
+    raw = bytes(g_res.cpu().numpy())
+    off = g_off.cpu().numpy()
+    assert [raw[off[i]:off[i + 1]].decode("latin-1") for i in range(len(sel))] == [seqs[int(j)] for j in sel]
 
 
 @pytest.mark.parametrize("a,k,tile", [(2, 6, 8192), (5, 3, 7), (1, 4, 16)])
@@ -359,3 +386,17 @@ def test_apply_tensor_cores_envelope_fallbacks():
     assert r.top1[3].item() == 0 and abs(r.score1[3].item() - 300 / (300 * 8.0)) < 1e-15
     M[2, 2] = 2 ** 40                                    # needs 6 digit planes
     assert E.prepare_annotations(M) is None
+
+
+@pytest.mark.parametrize("a,k", [(5, 3), (2, 9), (None, 5)])
+def test_kmer_totals_counts_only(a, k):
+    """skm_basis_accumulate without the first-position table == the count column of the full tables."""
+    rng = np.random.default_rng(k)
+    seqs = _rand_seqs(rng, 700, 0, 400)
+    batch = E.SequenceBatch.from_strings(seqs)
+    tab = E.alphabet_tables(a)
+    count, first = E.basis_tables(tab.nsym ** k, batch.device)
+    E.basis_accumulate(batch, a, k, count, first, 0)
+    assert torch.equal(E.kmer_totals(batch, a, k), count)
+    _, (si, pos, code, valid), _ = _codes_oracle(seqs, a, k)
+    assert np.array_equal(count.cpu().numpy(), np.bincount(code[valid].astype(np.int64), minlength=tab.nsym ** k))
