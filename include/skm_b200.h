@@ -187,9 +187,10 @@ SKM_API int skm_gather_sequences(const uint8_t *d_residues, const int64_t *d_off
                          skm_stream_t stream);
 
 /* Merge.merge_dataframes (learn.smk:467-494) for sparse matrices / fan-in of per-GPU lists:
- * entries with equal keys are summed; output sorted by key, capacity n, count in *d_n_out. */
+ * entries with equal keys are summed; output sorted by key, capacity n, count in *d_n_out.
+ * key_bound: exclusive upper bound of the keys (n_ann * S), 0 = unknown — limits the bits of the sort. */
 SKM_API size_t skm_coo_merge_workspace(int64_t n);
-SKM_API int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n,
+SKM_API int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n, uint64_t key_bound,
                   uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
                   void *workspace, size_t workspace_bytes, skm_stream_t stream);
 

@@ -15,6 +15,14 @@ reference computes from the ``seq-annotation-scores-*.csv`` files of eval_apply:
                                   bins repeat the last value); weight = number of Known rows, sum = rows per
                                   bin; optional merge with ONE prior global-confidence file.
 
+Third-party arithmetic at the file boundary: the reference reads the score files and the prior confidence file with
+``pandas.read_csv`` (C engine, default ``float_precision``), whose float converter is NOT round-trip exact — it
+accumulates at most 17 digits in a double and divides once by a power of ten (pandas/_libs/src/parser/tokenizer.c,
+``precise_xstrtod``); about a third of 17-digit reprs come back one ulp off (``"0.9099999999999999"`` -> 0.91), which
+moves exact ties and bin edges.  ``pandas_float`` restates that converter (pinned against pandas 3.0.2 on 200 k
+strings, tests/test_oracle_golden.py) and ``read_scores_csv`` / ``read_global_csv`` use it, so the oracle sees the
+numbers the reference sees.
+
 Pinned against the unmodified reference run in the build container (tests/golden/make_golden_eval.py ->
 tests/golden/eval_*.npz; tests/test_oracle_golden.py).
 """
@@ -26,6 +34,84 @@ import numpy as np
 
 NBINS = 101
 POSSIBLE = np.array([round(x * 0.01, 2) for x in range(NBINS)], dtype=np.float64)   # learn.smk:1063
+
+
+def pandas_float(txt: str) -> float:
+    """``precise_xstrtod`` of pandas' C parser (the default float converter of read_csv): sign, at most 17 digits
+    accumulated as ``number * 10 + digit`` in a double (further integer digits bump the exponent, further decimals
+    are dropped), optional exponent, then ONE multiplication / division by the double 1e|exponent|."""
+    p, n, neg = 0, len(txt), False
+    if p < n and txt[p] in "+-":
+        neg = txt[p] == "-"
+        p += 1
+    number, exponent, num_digits, num_decimals, max_digits = 0.0, 0, 0, 0, 17
+    while p < n and txt[p].isdigit():
+        if num_digits < max_digits:
+            number = number * 10.0 + (ord(txt[p]) - 48)
+            num_digits += 1
+        else:
+            exponent += 1
+        p += 1
+    if p < n and txt[p] == ".":
+        p += 1
+        while num_digits < max_digits and p < n and txt[p].isdigit():
+            number = number * 10.0 + (ord(txt[p]) - 48)
+            p += 1
+            num_digits += 1
+            num_decimals += 1
+        while p < n and txt[p].isdigit():
+            p += 1
+        exponent -= num_decimals
+    if neg:
+        number = -number
+    if p < n and txt[p] in "eE":
+        p += 1
+        eneg = False
+        if p < n and txt[p] in "+-":
+            eneg = txt[p] == "-"
+            p += 1
+        e = 0
+        while p < n and txt[p].isdigit():
+            e = e * 10 + (ord(txt[p]) - 48)
+            p += 1
+        exponent += -e if eneg else e
+    if exponent > 308:
+        return float("inf")
+    if exponent > 0:
+        return number * float("1e%d" % exponent)
+    if exponent < -308:
+        return 0.0 if exponent < -616 else number / float("1e%d" % (-308 - exponent)) / 1e308
+    return number / float("1e%d" % (-exponent))
+
+
+_NA = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>", "N/A", "NA", "NULL",
+       "NaN", "None", "n/a", "nan", "null"}          # pandas' default na_values
+
+
+def _cell(v: str) -> float:
+    return np.nan if v in _NA else pandas_float(v)
+
+
+def read_scores_csv(text: str):
+    """A seq-annotation-scores CSV as the reference's read_csv sees it -> (S float64 [Q, A], row labels, column names)."""
+    import csv
+    import io
+
+    r = list(csv.reader(io.StringIO(text)))
+    ix = r[0].index("__index_level_0__")
+    cols = [c for i, c in enumerate(r[0]) if i != ix]
+    S = np.array([[_cell(v) for i, v in enumerate(x) if i != ix] for x in r[1:]], dtype=np.float64).reshape(len(r) - 1, len(cols))
+    return S, [x[ix] for x in r[1:]], cols
+
+
+def read_global_csv(text: str) -> Dict[str, np.ndarray]:
+    """A global-confidence-scores CSV (prior) as the reference's read_csv sees it."""
+    import csv
+    import io
+
+    r = list(csv.reader(io.StringIO(text)))
+    a = np.array([[_cell(v) for v in x] for x in r[1:]], dtype=np.float64).reshape(len(r) - 1, len(r[0]))
+    return {h: a[:, i] for i, h in enumerate(r[0])}
 
 
 def top_two_values(S: np.ndarray):

@@ -14,7 +14,6 @@ Multi-GPU: histograms are summed with one all_reduce.
 """
 from __future__ import annotations
 
-import csv as _csv
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -144,20 +143,14 @@ class ConfidenceAccumulator:
                 self._f[i] += hist_false[j]
 
     def add_scores_csv(self, path: str) -> None:
-        """A seq-annotation-scores CSV as the reference reads it (read_and_transform_input_data)."""
-        with open(path, newline="") as f:
-            reader = _csv.reader(f)
-            header = next(reader)
-            ix = header.index(INDEX_COL)
-            cols = [c for i, c in enumerate(header) if i != ix]
-            labels, data = [], []
-            for rec in reader:
-                if not rec:
-                    continue
-                labels.append(rec[ix])
-                data.append([float(v) if v != "" else np.nan for i, v in enumerate(rec) if i != ix])
-        S = np.array(data, dtype=np.float64).reshape(len(labels), len(cols))
-        self.add(top2_rows(torch.from_numpy(S).to(E._require_cuda())), labels, cols)
+        """A seq-annotation-scores CSV exactly as the reference reads it (read_and_transform_input_data,
+        learn.smk:964-970): pandas' C parser — its default float converter is not round-trip exact (about a third of
+        17-digit values come back one ulp off), and exact ties / bin edges depend on it."""
+        import pandas as pd
+
+        frame = pd.read_csv(path, index_col=INDEX_COL, header=0, engine="c")
+        S = np.ascontiguousarray(frame.values, dtype=np.float64)
+        self.add(top2_rows(torch.from_numpy(S).to(E._require_cuda())), [str(x) for x in frame.index], [str(c) for c in frame.columns])
 
     def finalize(self, prior: Optional[Dict[str, np.ndarray]] = None, modifier: float = 1.0) -> EvalResult:
         rows = sorted(self._names)
@@ -198,20 +191,15 @@ def _interpolate_linear(y: np.ndarray) -> np.ndarray:
 
 
 def read_global_confidence(path: str) -> Dict[str, np.ndarray]:
-    """global-confidence-scores.csv (Difference, confidence, weight, sum; 101 rows)."""
-    with open(path, newline="") as f:
-        reader = _csv.reader(f)
-        header = next(reader)
-        text = [rec for rec in reader if rec]
-    arr = np.array([[float(v) if v != "" else np.nan for v in rec] for rec in text], dtype=np.float64).reshape(-1, len(header))
-    col = {h: arr[:, i] for i, h in enumerate(header)}
+    """global-confidence-scores.csv (Difference, confidence, weight, sum; 101 rows) as the reference reads its
+    prior (``pd.read_csv(..., index_col="Difference")``, learn.smk:1264-1266): same parser, same integer / float
+    column typing."""
+    import pandas as pd
 
-    def is_int(name):       # pandas.read_csv infers int64 when every cell is an integer literal
-        i = header.index(name)
-        return all(rec[i].lstrip("+-").isdigit() for rec in text)
-
-    return {"Difference": col["Difference"], "confidence": col["confidence"], "weight": col["weight"], "sum": col["sum"],
-            "weight_is_int": is_int("weight"), "sum_is_int": is_int("sum")}
+    t = pd.read_csv(path, index_col="Difference")
+    return {"Difference": t.index.to_numpy(dtype=np.float64), "confidence": t["confidence"].to_numpy(dtype=np.float64),
+            "weight": t["weight"].to_numpy(dtype=np.float64), "sum": t["sum"].to_numpy(dtype=np.float64),
+            "weight_is_int": t["weight"].dtype.kind in "iu", "sum_is_int": t["sum"].dtype.kind in "iu"}
 
 
 def _num(v: float, as_int: bool = False) -> str:

@@ -14,8 +14,9 @@
 // distinct entry written, read and written again.  Sequences longer than the warp buffer (1024 windows; ~2 % of
 // UniRef-like proteins) are queued and handled by one CTA each (8192 keys in shared memory; beyond that the network
 // runs on a global scratch row).
-// 64-bit keys (code spaces up to 2^64 - 1) use the same kernel; with a basis given as a sorted code list the head of
-// every run is looked up (bucketed binary search) and runs outside the basis are dropped.
+// 64-bit keys (code spaces up to 2^64 - 1) use the same kernel; with a basis given as a sorted code list every
+// temporary entry is looked up in a second, fully occupied pass (bucketed binary search) and the compaction drops the
+// entries outside the basis.
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
@@ -90,16 +91,16 @@ __device__ __forceinline__ void group_sort(KeyT *keys, int n, int g) {
 }
 
 // MODE 0: key = code.  MODE 1: key = col_of_code[code] (table basis; filtered codes never enter).
-// MODE 2: key = code, heads looked up in a SortedBasis (runs outside it dropped, column written to tmp_cols).
+// (A basis given as a sorted code list is applied afterwards by csr_lookup_kernel: a separate, fully occupied pass
+// hides the latency of the dependent look-up loads that 24 sorting warps per SM could not.)
 // LONG = false: one warp per sequence, sequences with more than kcap windows are appended to long_list.
 // LONG = true : one CTA per queued sequence.
 template <typename KeyT, int MODE, bool LONG>
 __global__ void __launch_bounds__(LONG ? CS_LONG_THREADS : 32 * CS_WARPS)
 csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
                 const uint8_t *__restrict__ lut, KeyT nsym, int k, KeyT pow_k1, const int32_t *__restrict__ col_of_code,
-                SortedBasis sb, int kcap, int64_t *long_list, unsigned long long *n_long, KeyT *gscratch, int64_t gscratch_stride,
-                KeyT *__restrict__ tmp_keys, int32_t *__restrict__ tmp_cols, int32_t *__restrict__ tmp_vals,
-                int64_t *__restrict__ rowcount) {
+                int kcap, int64_t *long_list, unsigned long long *n_long, KeyT *gscratch, int64_t gscratch_stride,
+                KeyT *__restrict__ tmp_keys, int32_t *__restrict__ tmp_vals, int64_t *__restrict__ rowcount) {
     constexpr int GT = LONG ? CS_LONG_THREADS : 32;
     constexpr int SEG = GT * CS_C;
     constexpr int SYM_BYTES = ts_sym_bytes(SEG);
@@ -225,12 +226,10 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
             const int p = p0 + g;
             KeyT key = NONE;
             bool head = false;
-            int32_t col = -1;
             int len = 0;
             if (p < n) {
                 key = keys[p];
                 head = key != NONE && (p == 0 || keys[p - 1] != key);
-                if (head && MODE == 2 && sb.codes) { col = sorted_lookup(sb, uint64_t(key)); head = col >= 0; }
                 if (head) {
                     int q = p + 1;
                     while (q < n && keys[q] == key) ++q;
@@ -256,7 +255,6 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
             }
             if (head) {
                 tmp_keys[b + slot] = key;
-                if (MODE == 2 && tmp_cols) tmp_cols[b + slot] = col;
                 tmp_vals[b + slot] = len;
             }
             total += round;
@@ -266,9 +264,33 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
     }
 }
 
-// out[rowptr[s] + j] = tmp[off[s] + j] for j < rowptr[s+1] - rowptr[s]; one warp per row
-template <typename KeyT>
-__global__ void __launch_bounds__(256) csr_compact_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ rowptr, int64_t nseq,
+// basis look-up of every temporary entry: tmp_cols[off[s] + j] = column of tmp_keys[off[s] + j] or -1;
+// kept[s + 1] = entries of row s the basis holds.  One warp per row, one entry per lane: every lane runs its own
+// (bucketed) binary search, 64 warps per SM hide the dependent loads.
+__global__ void __launch_bounds__(256) csr_lookup_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ rowcount, int64_t nseq,
+                                                         const uint64_t *__restrict__ tmp_keys, SortedBasis sb,
+                                                         int32_t *__restrict__ tmp_cols, int64_t *__restrict__ kept) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t s = warp; s < nseq; s += nwarps) {
+        const int64_t src = __ldg(off + s), cnt = rowcount[s + 1];
+        int64_t n_kept = 0;
+        for (int64_t j0 = 0; j0 < cnt; j0 += 32) {
+            const int64_t j = j0 + lane;
+            int32_t col = -1;
+            if (j < cnt) { col = sorted_lookup(sb, tmp_keys[src + j]); tmp_cols[src + j] = col; }
+            n_kept += __popc(__ballot_sync(FULL, col >= 0));
+        }
+        if (lane == 0) kept[s + 1] = n_kept;
+    }
+}
+
+// out[rowptr[s] + j'] = tmp[off[s] + j] for the entries j < rowcount[s + 1] of row s (all of them, or with FILTER only
+// those with tmp_cols >= 0, order preserved); one warp per row
+template <typename KeyT, bool FILTER>
+__global__ void __launch_bounds__(256) csr_compact_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ rowcount,
+                                                          const int64_t *__restrict__ rowptr, int64_t nseq,
                                                           const KeyT *__restrict__ tmp_keys, const int32_t *__restrict__ tmp_cols,
                                                           const int32_t *__restrict__ tmp_vals, KeyT *__restrict__ keys_out,
                                                           uint32_t *__restrict__ cols_out, int32_t *__restrict__ vals_out) {
@@ -276,11 +298,21 @@ __global__ void __launch_bounds__(256) csr_compact_kernel(const int64_t *__restr
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     for (int64_t s = warp; s < nseq; s += nwarps) {
-        const int64_t src = __ldg(off + s), dst = rowptr[s], cnt = rowptr[s + 1] - dst;
-        for (int64_t j = lane; j < cnt; j += 32) {
-            if (keys_out) keys_out[dst + j] = tmp_keys[src + j];
-            if (cols_out) cols_out[dst + j] = uint32_t(tmp_cols[src + j]);
-            vals_out[dst + j] = tmp_vals[src + j];
+        const int64_t src = __ldg(off + s), cnt = rowcount[s + 1];
+        int64_t dst = rowptr[s];
+        for (int64_t j0 = 0; j0 < cnt; j0 += 32) {
+            const int64_t j = j0 + lane;
+            int32_t col = 0;
+            bool keep = j < cnt;
+            if (keep && FILTER) { col = tmp_cols[src + j]; keep = col >= 0; }
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int64_t d = dst + __popc(m & ((1u << lane) - 1u));
+                if (keys_out) keys_out[d] = tmp_keys[src + j];
+                if (FILTER && cols_out) cols_out[d] = uint32_t(col);
+                vals_out[d] = tmp_vals[src + j];
+            }
+            dst += __popc(m);
         }
     }
 }
@@ -308,7 +340,7 @@ struct CsPlan {
     size_t key_bytes;
     int long_grid;
     int64_t gscratch_stride;     // keys per CTA of the long kernel's global scratch (0: none needed)
-    size_t tmp_keys, tmp_cols, tmp_vals, rowcount, long_list, n_long, gscratch, bucket, scan_temp;
+    size_t tmp_keys, tmp_cols, tmp_vals, rowcount, kept, long_list, n_long, gscratch, bucket, scan_temp;
     size_t total;
 };
 
@@ -325,6 +357,7 @@ static CsPlan cs_plan(int64_t nres, int64_t nseq, int64_t max_len, size_t key_by
     p.tmp_cols = take(with_cols ? size_t(nres) * 4 : 0);
     p.tmp_vals = take(size_t(nres) * 4);
     p.rowcount = take(size_t(nseq + 1) * 8);
+    p.kept = take(with_cols ? size_t(nseq + 1) * 8 : 0);
     p.long_list = take(size_t(nseq) * 8);
     p.n_long = take(8);
     p.gscratch = take(size_t(p.gscratch_stride) * key_bytes * p.long_grid);
@@ -336,12 +369,12 @@ static CsPlan cs_plan(int64_t nres, int64_t nseq, int64_t max_len, size_t key_by
 
 template <typename KeyT, int MODE>
 static int cs_run(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq, const uint8_t *d_lut, int nsym, int k,
-                  const int32_t *d_col_of_code, SortedBasis sb, int64_t max_len, const CsPlan &pl, char *ws, int64_t *d_rowptr,
+                  const int32_t *d_col_of_code, const SortedBasis *sb, int64_t max_len, const CsPlan &pl, char *ws, int64_t *d_rowptr,
                   KeyT *d_keys_out, uint32_t *d_cols_out, int32_t *d_vals, cudaStream_t st) {
     KeyT pow_k1 = 1;
     for (int i = 0; i + 1 < k; ++i) pow_k1 *= KeyT(nsym);
     KeyT *tmp_keys = reinterpret_cast<KeyT *>(ws + pl.tmp_keys);
-    int32_t *tmp_cols = (MODE == 2 && d_cols_out) ? reinterpret_cast<int32_t *>(ws + pl.tmp_cols) : nullptr;
+    int32_t *tmp_cols = sb ? reinterpret_cast<int32_t *>(ws + pl.tmp_cols) : nullptr;
     int32_t *tmp_vals = reinterpret_cast<int32_t *>(ws + pl.tmp_vals);
     int64_t *rowcount = reinterpret_cast<int64_t *>(ws + pl.rowcount);
     int64_t *long_list = reinterpret_cast<int64_t *>(ws + pl.long_list);
@@ -359,8 +392,8 @@ static int cs_run(const uint8_t *d_residues, int64_t nres, const int64_t *d_offs
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
         const int grid = (int)std::min<int64_t>((nseq + CS_WARPS - 1) / CS_WARPS, int64_t(sm_count()) * per_sm);
-        kern<<<grid, 32 * CS_WARPS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, sb, CS_KCAP_W,
-                                                 long_list, n_long, nullptr, 0, tmp_keys, tmp_cols, tmp_vals, rowcount);
+        kern<<<grid, 32 * CS_WARPS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, CS_KCAP_W,
+                                                 long_list, n_long, nullptr, 0, tmp_keys, tmp_vals, rowcount);
         SKM_LAUNCH_CHECK("csr_sort_kernel(warp)");
     }
     // long sequences (the list may be empty: the CTAs then exit at once)
@@ -369,13 +402,22 @@ static int cs_run(const uint8_t *d_residues, int64_t nres, const int64_t *d_offs
         const size_t smem = size_t(CS_KCAP_C) * sizeof(KeyT) + SYM_C;
         auto kern = csr_sort_kernel<KeyT, MODE, true>;
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<pl.long_grid, CS_LONG_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, sb, CS_KCAP_C,
-                                                           long_list, n_long, gscratch, pl.gscratch_stride, tmp_keys, tmp_cols, tmp_vals, rowcount);
+        kern<<<pl.long_grid, CS_LONG_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, KeyT(nsym), k, pow_k1, d_col_of_code, CS_KCAP_C,
+                                                           long_list, n_long, gscratch, pl.gscratch_stride, tmp_keys, tmp_vals, rowcount);
         SKM_LAUNCH_CHECK("csr_sort_kernel(long)");
     }
+    const int64_t *counts = rowcount;
+    if (sb) {
+        int64_t *kept = reinterpret_cast<int64_t *>(ws + pl.kept);
+        SKM_CUDA_TRY(cudaMemsetAsync(kept, 0, 8, st));
+        csr_lookup_kernel<<<sm_count() * 8, 256, 0, st>>>(d_offsets, rowcount, nseq, reinterpret_cast<const uint64_t *>(tmp_keys), *sb, tmp_cols, kept);
+        SKM_LAUNCH_CHECK("csr_lookup_kernel");
+        counts = kept;
+    }
     size_t temp_bytes = pl.total - pl.scan_temp;
-    SKM_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + pl.scan_temp, temp_bytes, rowcount, d_rowptr, nseq + 1, st));
-    csr_compact_kernel<KeyT><<<sm_count() * 8, 256, 0, st>>>(d_offsets, d_rowptr, nseq, tmp_keys, tmp_cols, tmp_vals, d_keys_out, d_cols_out, d_vals);
+    SKM_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + pl.scan_temp, temp_bytes, counts, d_rowptr, nseq + 1, st));
+    if (sb) csr_compact_kernel<KeyT, true><<<sm_count() * 8, 256, 0, st>>>(d_offsets, rowcount, d_rowptr, nseq, tmp_keys, tmp_cols, tmp_vals, d_keys_out, d_cols_out, d_vals);
+    else csr_compact_kernel<KeyT, false><<<sm_count() * 8, 256, 0, st>>>(d_offsets, rowcount, d_rowptr, nseq, tmp_keys, nullptr, tmp_vals, d_keys_out, nullptr, d_vals);
     SKM_LAUNCH_CHECK("csr_compact_kernel");
     return SKM_OK;
 }
@@ -430,11 +472,10 @@ int skm_count_csr_sorted(const uint8_t *d_residues, int64_t nres, const int64_t 
         sb.bucket = bucket;
     }
     if (!wide) {
-        if (d_col_of_code) return cs_run<uint32_t, 1>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, sb, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
-        return cs_run<uint32_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
+        if (d_col_of_code) return cs_run<uint32_t, 1>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_col_of_code, nullptr, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
+        return cs_run<uint32_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, nullptr, max_len, pl, ws, d_rowptr, (uint32_t *)d_keys_out, nullptr, d_vals, st);
     }
-    if (d_sorted_codes) return cs_run<uint64_t, 2>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint64_t *)d_keys_out, d_cols_out, d_vals, st);
-    return cs_run<uint64_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, sb, max_len, pl, ws, d_rowptr, (uint64_t *)d_keys_out, nullptr, d_vals, st);
+    return cs_run<uint64_t, 0>(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, nullptr, d_sorted_codes ? &sb : nullptr, max_len, pl, ws, d_rowptr, (uint64_t *)d_keys_out, d_cols_out, d_vals, st);
 }
 
 }  // extern "C"

@@ -470,7 +470,7 @@ size_t skm_coo_merge_workspace(int64_t n) {
     return 2 * al(size_t(n) * 8) + al(std::max(t_sort, t_red)) + 1024;
 }
 
-int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n, uint64_t *d_keys_out,
+int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n, uint64_t key_bound, uint64_t *d_keys_out,
                   int64_t *d_vals_out, int64_t *d_n_out, void *workspace, size_t workspace_bytes,
                   skm_stream_t stream) {
     using namespace skm;
@@ -487,7 +487,9 @@ int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n
     int64_t *sv = (int64_t *)(p + seg);
     void *temp = p + 2 * seg;
     size_t temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
-    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, d_keys_in, sk, d_vals_in, sv, n, 0, 64, st));
+    // keys are < key_bound (0 = unknown): the sort only needs its bits (35 of 64 for the C3 matrix)
+    const int end_bit = key_bound ? bits_for((unsigned __int128)key_bound) : 64;
+    SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, d_keys_in, sk, d_vals_in, sv, n, 0, end_bit, st));
     temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
     SKM_CUDA_TRY(cub::DeviceReduce::ReduceByKey(temp, temp_bytes, sk, d_keys_out, sv, d_vals_out, d_n_out, cub::Sum(), n, st));
     return SKM_OK;

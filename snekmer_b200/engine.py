@@ -653,8 +653,9 @@ def _chunks_by_residues(offsets_host: np.ndarray, max_res: int):
     return out
 
 
-def coo_merge(keys: torch.Tensor, vals: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Sum entries with equal keys; result sorted by key (Merge.merge_dataframes for sparse matrices)."""
+def coo_merge(keys: torch.Tensor, vals: torch.Tensor, key_bound: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sum entries with equal keys; result sorted by key (Merge.merge_dataframes for sparse matrices).
+    key_bound: exclusive upper bound of the keys (n_ann * S) when known — the sort then runs over its bits only."""
     dev = _require_cuda(keys.device)
     n = keys.numel()
     keys, vals = keys.contiguous(), vals.contiguous()
@@ -663,7 +664,7 @@ def coo_merge(keys: torch.Tensor, vals: torch.Tensor) -> Tuple[torch.Tensor, tor
     ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     ov = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     dn = torch.zeros(1, dtype=torch.int64, device=dev)
-    check(lib().skm_coo_merge(_ptr(keys), _ptr(vals), n, _ptr(ok), _ptr(ov), _ptr(dn), _ptr(ws), ws_bytes, _stream()))
+    check(lib().skm_coo_merge(_ptr(keys), _ptr(vals), n, int(key_bound), _ptr(ok), _ptr(ov), _ptr(dn), _ptr(ws), ws_bytes, _stream()))
     m = int(dn.item())
     return ok[:m].clone(), ov[:m].clone()
 
@@ -752,7 +753,7 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
     if not parts_k:
         z = torch.zeros(0, dtype=torch.int64, device=dev)
         return z, z.clone()
-    return coo_merge(torch.cat(parts_k), torch.cat(parts_v))
+    return coo_merge(torch.cat(parts_k), torch.cat(parts_v), key_bound=n_ann * S)
 
 
 @dataclass
@@ -1122,4 +1123,4 @@ def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n
         return keys, vals
     bounds = [(n_ann * r // w) * S for r in range(w)] + [n_ann * S]
     k2, v2 = D.alltoall_coo_by_key_range(keys, vals, bounds)
-    return coo_merge(k2, v2)
+    return coo_merge(k2, v2, key_bound=n_ann * S)

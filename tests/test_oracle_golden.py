@@ -169,13 +169,7 @@ def _eval_fixture():
 
     d = np.load(os.path.join(GOLDEN, "eval_confidence.npz"))
     txt = lambda k: bytes(d[k]).decode()
-
-    def scores(t):
-        r = list(csv.reader(io.StringIO(t)))
-        ix = r[0].index("__index_level_0__")
-        cols = [c for i, c in enumerate(r[0]) if i != ix]
-        S = np.array([[float(v) if v != "" else np.nan for i, v in enumerate(x) if i != ix] for x in r[1:]])
-        return S, [x[ix] for x in r[1:]], cols
+    scores = EV.read_scores_csv
 
     def glob(t):
         r = list(csv.reader(io.StringIO(t)))
@@ -191,15 +185,34 @@ def _eval_fixture():
     return EV, txt, scores, glob, conf
 
 
+def test_pandas_float_restatement_matches_pandas():
+    """oracle.skm_evaluator.pandas_float == the float converter of pandas.read_csv (C engine, default precision),
+    which is what the reference's Evaluator reads its inputs with — and it is NOT float(): ~30 % of 17-digit reprs
+    come back one ulp off."""
+    import io
+    import random
+
+    import pandas as pd
+
+    from oracle import skm_evaluator as EV
+
+    rng = random.Random(3)
+    tests = [repr((rng.random() * 10 ** rng.randint(-8, 8)) * (-1 if rng.random() < 0.1 else 1)) for _ in range(40000)]
+    tests += ["1e-05", "2.5e-07", "1.0", "0.0", "-0.0", "1", "0.5", "123456789012345678", "1e22", "3.0000000000000004e-05",
+              "1e-300", "4.9e-324", "1.7976931348623157e308", "0.9099999999999999", "0.30000000000000004"]
+    got = pd.read_csv(io.StringIO("a\n" + "\n".join(tests) + "\n"), dtype=float)["a"].values
+    mine = np.array([EV.pandas_float(t) for t in tests])
+    assert np.array_equal(mine, got)
+    assert EV.pandas_float("0.9099999999999999") == 0.91 != float("0.9099999999999999")
+    assert (got != np.array([float(t) for t in tests])).mean() > 0.1
+
+
 @pytest.mark.parametrize("name,files,prior,mod", [("one", ["synA"], None, 1.0), ("two", ["synA", "synB"], None, 1.0),
                                                   ("tricky", ["tricky"], None, 1.0), ("tricky_first", ["tricky", "synA"], None, 1.0),
                                                   ("prior", ["synB"], "one", 0.5)])
 def test_evaluator_oracle_matches_reference_files(name, files, prior, mod):
     EV, txt, scores, glob, conf = _eval_fixture()
-    pr = None
-    if prior:
-        _, a = glob(txt(prior + "_glob"))
-        pr = dict(confidence=a[:, 1], weight=a[:, 2], sum=a[:, 3])
+    pr = EV.read_global_csv(txt(prior + "_glob")) if prior else None
     r = EV.evaluate([scores(txt(f + "_csv")) for f in files], pr, mod)
     lab, g = glob(txt(name + "_glob"))
     hdr, rows, c = conf(txt(name + "_conf"))
