@@ -3,7 +3,7 @@
  *
  * The reference (PNNL-CompBio/Snekmer 1.3.0) is pure Python and has no FFI; the
  * boundary it exposes is the Python module API (snekmer.vectorize.KmerVec,
- * snekmer.alphabet, snekmer.io) and the rule-body loops in snekmer/rules/*.smk.
+ * snekmer.alphabet, snekmer.io) and the rule-body loops in the snekmer/rules .smk files.
  * Each entry point below names the reference code it replaces (file:line under
  * /root/reference).  The Python package snekmer_b200 binds these with ctypes
  * (snekmer_b200/_native.py); INTEGRATION.md shows the reference-side stub.

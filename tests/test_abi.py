@@ -53,3 +53,24 @@ def test_compute_fails_loudly_without_gpu():
 
     with pytest.raises(E.SkmError):
         E.SequenceBatch.from_strings(["ACD"])
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/skm_b200.h compiles as C99 and a C program drives the host-only entry points through the .so."""
+    import shutil
+    import subprocess
+
+    from snekmer_b200 import _native, build
+
+    build.build()
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "host_only")
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cabi", "host_only.c"), "-o", exe, "-L", libdir, "-lskm_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "cabi ok" in r.stdout
