@@ -302,7 +302,7 @@ def run_learn(ctx, args):
         count = E.kmer_totals(batch, alphabet, k)                    # Totals row: occurrence counts over ALL sequences
         keys, vals = E.learn_sparse(batch, alphabet, k, d_ann, n_ann)
         if ctx.world > 1:
-            keys, vals = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
+            keys, vals, _ = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
             ctx.dist.all_reduce(count)
         state["nnz"] = keys.numel()
         state["totals"] = count

@@ -178,6 +178,25 @@ def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds
     return out_k, out_v
 
 
+def balanced_annotation_bounds(keys: torch.Tensor, S: int, n_ann: int) -> List[int]:
+    """W+1 annotation indices cutting [0, n_ann) into contiguous ranges with ~equal numbers of COO entries summed over
+    all ranks (`keys` = this rank's sorted keys ann * S + code).  One all_reduce of the per-annotation entry histogram;
+    identical on every rank.  Family sizes are Zipf-distributed: equal id ranges would give rank 0 most of the matrix."""
+    rank, w = world()
+    dev = keys.device
+    edges = torch.arange(n_ann + 1, dtype=torch.int64, device=dev) * int(S)
+    per_ann = torch.diff(torch.searchsorted(keys, edges))                      # local entries of every annotation
+    allreduce_sum_(per_ann)
+    csum = torch.cumsum(per_ann, 0)
+    total = int(csum[-1].item()) if n_ann else 0
+    targets = torch.tensor([total * r // w for r in range(1, w)], dtype=torch.int64, device=dev)
+    cuts = torch.searchsorted(csum, targets, right=False).tolist() if w > 1 and n_ann else []
+    bounds = [0] + [min(c + 1, n_ann) for c in cuts] + [n_ann]                  # the annotation that reaches the target closes its range
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
 def barrier() -> None:
     if world()[1] > 1:
         dist.barrier()

@@ -49,19 +49,29 @@ def main():
     # sparse learn: grouped 32-bit-key build on the local shard + all_to_all of COO runs by annotation range
     S = len(syms) ** k
     keys, vals = E.learn_sparse(batch, a, k, torch.from_numpy(ann[lo:hi]), n_ann)
-    keys, vals = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
-    a_lo, a_hi = n_ann * rank // world, n_ann * (rank + 1) // world
+    keys0, vals0 = keys, vals
+    keys, vals, (a_lo, a_hi) = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann, balance=False)
+    assert (a_lo, a_hi) == (n_ann * rank // world, n_ann * (rank + 1) // world)
+    kb, vb, (b_lo, b_hi) = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)          # ranges balanced by entry count
+    spans = [None] * world
+    torch.distributed.all_gather_object(spans, (b_lo, b_hi, int(kb.numel())))
+    assert spans[0][0] == 0 and spans[-1][1] == n_ann and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1)), spans
+    kbn = kb.cpu().numpy()
+    gotb = np.zeros((n_ann, S), dtype=np.int64)
+    gotb[kbn // S, kbn % S] = vb.cpu().numpy()
+    assert ((kbn // S >= b_lo) & (kbn // S < b_hi)).all(), "balanced exchange ranges"
     full = np.zeros((n_ann, S), dtype=np.int64)
     full[:, want_basis.astype(np.int64)] = want_M[:n_ann]
     kk = keys.cpu().numpy()
     got = np.zeros((n_ann, S), dtype=np.int64)
     got[kk // S, kk % S] = vals.cpu().numpy()
     assert np.all(kk[1:] > kk[:-1]) and (kk // S >= a_lo).all() and (kk // S < a_hi).all(), "sparse learn exchange ranges"
-    if mf == 0:
-        assert np.array_equal(got[a_lo:a_hi], full[a_lo:a_hi]), "sparse learn exchange"
-    else:   # the dense matrix only holds basis columns (count > min_filter); compare on those
-        cols = want_basis.astype(np.int64)
-        assert np.array_equal(got[a_lo:a_hi][:, cols], want_M[a_lo:a_hi]), "sparse learn exchange"
+    cols = want_basis.astype(np.int64)         # the dense matrix only holds basis columns (count > min_filter)
+    assert np.array_equal(got[a_lo:a_hi][:, cols], want_M[a_lo:a_hi]), "sparse learn exchange"
+    assert np.array_equal(gotb[b_lo:b_hi][:, cols], want_M[b_lo:b_hi]), "balanced sparse learn exchange"
+    if rank == 0:
+        sizes = [sp[2] for sp in spans]
+        print("balanced exchange entries per rank:", sizes)
     # apply, annotation-sharded: all queries everywhere, my slice of annotation rows
     qbatch = E.SequenceBatch.from_strings(seqs[:500])
     Q = E.count_dense(qbatch, a, k, basis)

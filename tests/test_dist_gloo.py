@@ -109,6 +109,21 @@ def _worker(rank, world, port, tmp):
         tot = torch.tensor([int(rv.sum()), int(cnt.sum())])
         dist.all_reduce(tot)
         assert tot[0].item() == tot[1].item()                 # nothing lost, nothing duplicated
+        # ---- the same exchange with ranges balanced by entry count (Zipf-sized annotations) ------------------------
+        zrng = np.random.default_rng(7 + rank)
+        wz = 1.0 / np.arange(1, 41) ** 1.3
+        za = zrng.choice(40, size=3000, p=wz / wz.sum()).astype(np.int64)
+        zk = np.unique(za * Sp + zrng.integers(0, Sp, size=3000))
+        zb = D.balanced_annotation_bounds(torch.from_numpy(zk), Sp, 40)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (zb, zk))
+        assert all(g[0] == zb for g in gathered) and zb[0] == 0 and zb[-1] == 40 and zb == sorted(zb)
+        allk = np.concatenate([g[1] for g in gathered])
+        per_range = [int(((allk // Sp >= zb[r]) & (allk // Sp < zb[r + 1])).sum()) for r in range(world)]
+        biggest = np.bincount(allk // Sp, minlength=40).max()
+        assert max(per_range) <= len(allk) / world + biggest, (per_range, biggest)       # within one annotation of even
+        even = [int(((allk // Sp >= 40 * r // world) & (allk // Sp < 40 * (r + 1) // world)).sum()) for r in range(world)]
+        assert max(per_range) <= max(even)
         # ---- wide basis fan-in: all_gather of per-rank (code, count, first) tables, merged by code -------------
         lc, li, lcnt = np.unique(code[valid], return_index=True, return_counts=True)
         lfirst = ((off[lo:hi + 1] - off[lo])[si[valid]] + pos[valid] + base)[li]
