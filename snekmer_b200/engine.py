@@ -1133,108 +1133,3 @@ def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n
     k2, v2 = D.alltoall_coo_by_key_range(keys, vals, [a * int(S) for a in ann_bounds])
     k3, v3 = coo_merge(k2, v2, key_bound=n_ann * S)
     return k3, v3, (ann_bounds[rank], ann_bounds[rank + 1])
-
-
-DENSE_ROW_MAX_K = 4096          # widest basis whose per-sequence counts are kept as dense rows by vectorize()
-
-
-@dataclass
-class Vectorized:
-    """Result of vectorize(): the basis and the per-sequence counts in the layout the basis size calls for."""
-    path: str                               # "dense" | "csr" | "wide"
-    basis: "Basis | WideBasis"
-    counts: Optional[torch.Tensor] = None   # dense: int32 [N, K]
-    rowptr: Optional[torch.Tensor] = None   # csr / wide: int64 [N+1]
-    cols: Optional[torch.Tensor] = None     #             int32 [nnz] basis column of every entry
-    vals: Optional[torch.Tensor] = None     #             int32 [nnz]
-    codes: Optional[torch.Tensor] = None    # wide only: int64 (uint64 pattern) [nnz]
-
-    @property
-    def K(self) -> int:
-        return self.basis.K
-
-    @property
-    def nnz(self) -> int:
-        return int(self.vals.numel()) if self.vals is not None else int((self.counts != 0).sum().item())
-
-
-def vectorize(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0,
-              dense_max_K: int = DENSE_ROW_MAX_K) -> Vectorized:
-    """Both passes of the vectorize rule (kmerize.smk:85-120) for ANY alphabet / k with nsym^k <= 2^64 - 1:
-    first-occurrence basis + per-sequence counts.  Code spaces up to 2^27 use the table kernels (dense rows while
-    the basis has at most `dense_max_K` columns, CSR beyond); larger ones the sort-based wide path."""
-    tab = alphabet_tables(alphabet, batch.device)
-    S = code_space(tab.nsym, k)
-    if S <= _native.SKM_DENSE_MAX_SPACE:
-        basis = build_basis(batch, alphabet, k, min_filter)
-        if basis.K <= dense_max_K:
-            return Vectorized("dense", basis, counts=count_dense(batch, alphabet, k, basis))
-        parts, base = [], 0
-        for lo, hi in _chunks_by_residues(batch.offsets_host, (1 << 30) - 16):
-            sub = batch if (lo == 0 and hi == batch.n) else _sub_batch(batch, lo, hi)
-            rp, c, v = count_csr(sub, alphabet, k, basis)
-            parts.append((rp[(1 if parts else 0):] + base, c, v))
-            base += int(v.numel())
-        if not parts:
-            z32 = torch.zeros(0, dtype=torch.int32, device=batch.device)
-            return Vectorized("csr", basis, rowptr=torch.zeros(1, dtype=torch.int64, device=batch.device), cols=z32, vals=z32.clone())
-        cat = (lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs))
-        return Vectorized("csr", basis, rowptr=cat([p[0] for p in parts]), cols=cat([p[1] for p in parts]), vals=cat([p[2] for p in parts]))
-    basis = build_basis_wide(batch, alphabet, k, min_filter)
-    rowptr, codes, cols, vals = count_csr_wide(batch, alphabet, k, basis)
-    return Vectorized("wide", basis, rowptr=rowptr, cols=cols, vals=vals, codes=codes)
-
-
-# ---------------------------------------------------------------------------
-# multi-GPU compositions (one process per GPU; collectives in dist.py)
-# ---------------------------------------------------------------------------
-def build_basis_distributed(batch: SequenceBatch, alphabet, k: int, min_filter: int = 0, res_base: Optional[int] = None) -> Basis:
-    """The basis of the CONCATENATION of all ranks' shards (rank order), identical on every rank:
-    local tables with global first positions, all_reduce(SUM / MIN), local finalisation."""
-    from . import dist as D
-
-    tab = alphabet_tables(alphabet, batch.device)
-    S = code_space(tab.nsym, k)
-    if S > _native.SKM_DENSE_MAX_SPACE:
-        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
-    if res_base is None:
-        res_base, _ = D.exclusive_prefix(batch.nres, batch.device)
-    count, first = basis_tables(S, batch.device)
-    basis_accumulate(batch, alphabet, k, count, first, res_base)
-    D.allreduce_basis_tables(count, first)
-    return basis_finalize(alphabet, k, count, first, min_filter)
-
-
-def learn_dense_distributed(batch: SequenceBatch, alphabet, k: int, basis: Optional[Basis], ann_id: torch.Tensor,
-                            n_ann: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """learn_dense on the local shard followed by the NCCL sum over ranks (the reference's
-    serial Merge step, learn.smk:467-494); every rank ends with the full matrix."""
-    from . import dist as D
-
-    M, totals = learn_dense(batch, alphabet, k, basis, ann_id, n_ann)
-    D.allreduce_sum_(M, totals)
-    return M, totals
-
-
-def apply_dense_annotation_sharded(Q: torch.Tensor, M_local: torch.Tensor, ann_base: int,
-                                   qnorm2: Optional[torch.Tensor] = None) -> ApplyResult:
-    """Every rank scores all queries against ITS rows of the annotation matrix; the per-shard
-    top-2 are all-gathered and merged (identical result on every rank)."""
-    from . import dist as D
-
-    r = apply_dense(Q, M_local, qnorm2=qnorm2)
-    idx, sc = D.allgather_top2(r.top1, r.top2, r.score1, r.score2, ann_base)
-    return merge_top2(idx, sc)
-
-
-def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Multi-GPU fan-in of sparse learn: annotations are split into equal ranges, rank r ends up with
-    the merged rows [n_ann*r/W, n_ann*(r+1)/W) of the matrix — the annotation sharding apply uses."""
-    from . import dist as D
-
-    rank, w = D.world()
-    if w == 1:
-        return keys, vals
-    bounds = [(n_ann * r // w) * S for r in range(w)] + [n_ann * S]
-    k2, v2 = D.alltoall_coo_by_key_range(keys, vals, bounds)
-    return coo_merge(k2, v2, key_bound=n_ann * S)
