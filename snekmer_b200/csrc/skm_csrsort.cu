@@ -6,8 +6,10 @@
 // from the residue bytes to its finished CSR row:
 //   scan     residues -> LUT -> symbols in the warp's shared buffer -> rolling codes (the count_dense_warp_kernel
 //            scanner); the key of every window (code, or basis column) goes to the warp's key buffer in shared memory;
-//   sort     bitonic network over the n keys in shared memory, all compare-exchanges ascending (flip formulation),
-//            so n need not be a power of two: partners at or beyond n act as +infinity;
+//   sort     bitonic network, all compare-exchanges ascending (flip formulation), so n need not be a power of two:
+//            partners at or beyond n act as +infinity.  32-bit keys of sequences up to 512 windows are sorted in
+//            REGISTERS (16 keys per lane, shuffles for the cross-lane steps: 75 instructions per key instead of ~250),
+//            everything else in shared memory;
 //   encode   run heads -> (key, run length) written to the sequence's own slots of a temporary CSR
 //            (tmp[off[s] + j]: a sequence never has more distinct k-mers than residues), distinct count -> rowcount.
 // A scan of rowcount gives rowptr and a copy kernel compacts the rows.  HBM traffic: residues once, 8-12 B per
@@ -27,6 +29,7 @@ namespace skm {
 constexpr int CS_C = 12;                       // residues per thread and segment (4 * odd)
 constexpr int CS_WARPS = 8;                    // warps (= sequences in flight) per CTA of the warp kernel
 constexpr int CS_KCAP_W = 1024;                // keys per warp buffer
+constexpr int CS_REG_KEYS = 512;               // sequences up to this many windows are sorted in registers (16 keys per lane)
 constexpr int CS_KCAP_C = 8192;                // keys per CTA buffer of the long-sequence kernel
 constexpr int CS_LONG_THREADS = 256;
 
@@ -90,6 +93,147 @@ __device__ __forceinline__ void group_sort(KeyT *keys, int n, int g) {
     }
 }
 
+// ---- register-resident warp sort (sequences of up to 1024 windows) --------------------------------------------
+// The network above costs ~11 SASS instructions per compare-exchange (two LDS, two STS, index arithmetic).  For the warp
+// kernel the keys are instead held in registers, blocked: element i = lane * R + r lives in register r of `lane`
+// (R = P / 32 for the padded size P).  Steps with distance < R are compare-exchanges between registers of one lane
+// (one min + one max per pair); steps with distance >= R exchange with lane ^ (distance / R) by shuffle and keep the
+// minimum or the maximum (2 instructions per key).  Same flip formulation, so everything is ascending and the
+// all-ones padding / invalid key sorts last.  P = 512: 75 instructions per key against ~250 through shared memory.
+__device__ __forceinline__ uint32_t shfl_xor_key(uint32_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
+__device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(FULL, uint32_t(v), m), hi = __shfl_xor_sync(FULL, uint32_t(v >> 32), m);
+    return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint32_t shfl_up_key(uint32_t v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ uint64_t shfl_up_key(uint64_t v) {
+    const uint32_t lo = __shfl_up_sync(FULL, uint32_t(v), 1), hi = __shfl_up_sync(FULL, uint32_t(v >> 32), 1);
+    return (uint64_t(hi) << 32) | lo;
+}
+template <typename KeyT> __device__ __forceinline__ void reg_ce(KeyT &a, KeyT &b) {
+    const KeyT lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+// one half-cleaner step at distance 2^LD, then the smaller distances (compile-time recursion: every register index
+// is a constant, so the key array stays in registers)
+template <typename KeyT, int R, int LD>
+__device__ __forceinline__ void sort_clean(KeyT (&key)[R], int lane) {
+    if constexpr (LD >= 0) {
+        constexpr int d = 1 << LD;
+        if constexpr (d >= R) {                         // partner lane ^ (d / R), same register
+            constexpr int m = d / R;
+            const bool lower = (lane & m) == 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const KeyT o = shfl_xor_key(key[r], m), a = key[r];
+                key[r] = lower ? (a < o ? a : o) : (a < o ? o : a);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((r & d) == 0) reg_ce(key[r], key[r + d]);
+        }
+        sort_clean<KeyT, R, LD - 1>(key, lane);
+    }
+}
+// stage k = 2^LK: flip step, half-cleaners, then the next stage up to 2^LOGP = 32 * R
+template <typename KeyT, int R, int LK, int LOGP>
+__device__ __forceinline__ void sort_stage(KeyT (&key)[R], int lane) {
+    if constexpr (LK <= LOGP) {
+        constexpr int k = 1 << LK;
+        if constexpr (k <= R) {                         // flip inside a lane: t <-> k-1-t in every block of k registers
+#pragma unroll
+            for (int b0 = 0; b0 < R; b0 += k)
+#pragma unroll
+                for (int t = 0; t < k / 2; ++t) reg_ce(key[b0 + t], key[b0 + k - 1 - t]);
+        } else {                                        // flip across lanes: (lane, r) <-> (mirrored lane, R-1-r)
+            constexpr int L = k / R, m = L - 1;
+            const bool lower = (lane & (L >> 1)) == 0;
+            if constexpr (R == 1) {
+                const KeyT o = shfl_xor_key(key[0], m), a = key[0];
+                key[0] = lower ? (a < o ? a : o) : (a < o ? o : a);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R / 2; ++r) {
+                    const KeyT o1 = shfl_xor_key(key[R - 1 - r], m), o2 = shfl_xor_key(key[r], m);
+                    const KeyT a = key[r], c = key[R - 1 - r];
+                    key[r] = lower ? (a < o1 ? a : o1) : (a < o1 ? o1 : a);
+                    key[R - 1 - r] = lower ? (c < o2 ? c : o2) : (c < o2 ? o2 : c);
+                }
+            }
+        }
+        sort_clean<KeyT, R, LK - 2>(key, lane);
+        sort_stage<KeyT, R, LK + 1, LOGP>(key, lane);
+    }
+}
+template <typename KeyT, int R>
+__device__ __forceinline__ void warp_sort_regs(KeyT (&key)[R], int lane) {
+    constexpr int LOGP = (R == 1 ? 5 : R == 2 ? 6 : R == 4 ? 7 : R == 8 ? 8 : R == 16 ? 9 : 10);      // log2(32 * R)
+    sort_stage<KeyT, R, 1, LOGP>(key, lane);
+}
+
+// padded index of key i in the warp's shared buffer: one spare word per 32 keeps both the scan's writes and the
+// blocked reads (lane * R + r) spread over the banks
+__device__ __forceinline__ int kpad(int i) { return i + (i >> 5); }
+
+// keys[kpad(0 .. n)) (unsorted, invalid windows = NONE) -> sorted in registers -> run heads with their lengths written to
+// tmp_keys / tmp_vals [b + slot]; returns the number of runs (= distinct valid keys).  Whole warp, converged.
+template <typename KeyT, int R>
+__device__ __forceinline__ int warp_sort_encode(const KeyT *keys, int n, int lane, int64_t b, KeyT *__restrict__ tmp_keys,
+                                                int32_t *__restrict__ tmp_vals) {
+    constexpr KeyT NONE = key_none<KeyT>::v;
+    KeyT key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = lane * R + r;
+        key[r] = (i < n) ? keys[kpad(i)] : NONE;
+    }
+    warp_sort_regs<KeyT, R>(key, lane);
+    // run heads; NONE keys are at the end
+    const KeyT up = shfl_up_key(key[R - 1]);             // last key of the previous lane
+    int nheads = 0, nvalid = 0, first_head = 0x7FFFFFFF;
+    uint32_t headmask = 0;                              // bit r: register r starts a run (R <= 32)
+    {
+        const bool valid = key[0] != NONE;
+        const bool head = valid && (lane == 0 || key[0] != up);
+        nvalid += valid;
+        if (head) { headmask |= 1u; first_head = lane * R; ++nheads; }
+    }
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+        const bool valid = key[r] != NONE;
+        const bool head = valid && key[r] != key[r - 1];
+        nvalid += valid;
+        if (head) { headmask |= 1u << r; if (nheads == 0) first_head = lane * R + r; ++nheads; }
+    }
+    // exclusive prefix of the head counts (slot base of this lane) and the total
+    int incl = nheads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int tot_valid = nvalid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot_valid += __shfl_xor_sync(FULL, tot_valid, o);
+    // position of the next run head after this lane: suffix minimum of the lanes' first heads
+    int suf = first_head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(FULL, suf, o); if (lane + o < 32 && t < suf) suf = t; }
+    int next = __shfl_down_sync(FULL, suf, 1);
+    if (lane == 31 || next == 0x7FFFFFFF) next = tot_valid;          // the last run ends where the valid keys end
+    int slot = (incl - nheads) + nheads - 1;
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+        if (headmask & (1u << r)) {
+            const int idx = lane * R + r;
+            tmp_keys[b + slot] = key[r];
+            tmp_vals[b + slot] = next - idx;
+            next = idx;
+            --slot;
+        }
+    }
+    return total;
+}
+
 // MODE 0: key = code.  MODE 1: key = col_of_code[code] (table basis; filtered codes never enter).
 // (A basis given as a sorted code list is applied afterwards by csr_lookup_kernel: a separate, fully occupied pass
 // hides the latency of the dependent look-up loads that 24 sorting warps per SM could not.)
@@ -111,9 +255,10 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
     const int grp = LONG ? 0 : (threadIdx.x >> 5);
     const int g = LONG ? int(threadIdx.x) : int(threadIdx.x & 31);
     const int lane = threadIdx.x & 31;
-    uint8_t *mine = s_raw + size_t(grp) * (size_t(kcap) * sizeof(KeyT) + SYM_BYTES);
+    const size_t key_bytes = size_t(LONG ? kcap : kcap + (kcap >> 5)) * sizeof(KeyT);      // warp buffers are padded (kpad)
+    uint8_t *mine = s_raw + size_t(grp) * (key_bytes + SYM_BYTES);
     KeyT *s_key = reinterpret_cast<KeyT *>(mine);
-    uint8_t *s_sym = mine + size_t(kcap) * sizeof(KeyT);
+    uint8_t *s_sym = mine + key_bytes;
     uint32_t sym_addr = smem_addr(s_sym);
     asm volatile("" : "+r"(sym_addr));
     ts_lut_init(s_lut, lut);
@@ -145,6 +290,9 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
             continue;
         }
         KeyT *keys = (LONG && n > kcap) ? gscratch + int64_t(blockIdx.x) * gscratch_stride : s_key;
+        // 32-bit keys of sequences up to 512 windows are sorted in registers (padded buffer layout); 64-bit keys stay on
+        // the shared-memory network (twice the shuffles and 80 registers made the register version slower: 4.9 vs 3.8 ms)
+        const bool in_regs = !LONG && sizeof(KeyT) == 4 && n <= CS_REG_KEYS;
         // ---- scan: key of the window ending at residue b + (k-1) + i goes to keys[i] ----
         bool first = true;
         uint32_t tail0 = 0, tail1 = 0;
@@ -206,7 +354,7 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
                             if (MODE == 1) { const int32_t c = __ldg(col_of_code + code); if (c >= 0) key = KeyT(c); }
                             else key = code;
                         }
-                        keys[widx] = key;
+                        keys[in_regs ? int64_t(kpad(int(widx))) : widx] = key;
                     }
                     code -= KeyT(lds_u8<0>(p - back)) * pow_k1;
                 }
@@ -218,10 +366,14 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
             first = false;
             a = a2;
         }
-        // ---- sort ----
+        int total = 0;
+        if (sizeof(KeyT) == 4 && in_regs) {
+            // ---- sort + encode in registers (one instantiation: several unrolled networks thrash the instruction cache) ----
+            total = warp_sort_encode<KeyT, CS_REG_KEYS / 32>(keys, n, lane, b, tmp_keys, tmp_vals);
+        } else {
+        // ---- sort (shared / global memory network) ----
         group_sort<KeyT, GT>(keys, n, g);
         // ---- encode: run heads -> tmp[b + slot] ----
-        int total = 0;
         for (int p0 = 0; p0 < n; p0 += GT) {
             const int p = p0 + g;
             KeyT key = NONE;
@@ -258,6 +410,7 @@ csr_sort_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__
                 tmp_vals[b + slot] = len;
             }
             total += round;
+        }
         }
         if (g == 0) rowcount[s + 1] = total;
         gsync<GT>();                        // the key buffer is rewritten by the next sequence
@@ -385,7 +538,7 @@ static int cs_run(const uint8_t *d_residues, int64_t nres, const int64_t *d_offs
     // warp kernel
     {
         constexpr int SYM_W = ts_sym_bytes(32 * CS_C);
-        const size_t smem = size_t(CS_WARPS) * (size_t(CS_KCAP_W) * sizeof(KeyT) + SYM_W);
+        const size_t smem = size_t(CS_WARPS) * (size_t(CS_KCAP_W + (CS_KCAP_W >> 5)) * sizeof(KeyT) + SYM_W);
         auto kern = csr_sort_kernel<KeyT, MODE, false>;
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = int((227 * 1024) / (smem + 1536));

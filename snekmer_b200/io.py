@@ -119,7 +119,12 @@ def parse_fasta_bytes(text: bytes, threads: int = 0, pinned: bool = False):
     check(lib().skm_fasta_pack(tp, n, int(threads), residues.ctypes.data if nres else None, offsets.ctypes.data,
                                ids_buf.ctypes.data if idb else None, id_off.ctypes.data))
     raw = ids_buf.tobytes()
-    ids = [raw[id_off[i]:id_off[i + 1]].decode("utf-8", "replace") for i in range(nseq)]
+    bounds = id_off.tolist()
+    if raw.isascii():                   # byte offsets are character offsets: one decode, then slices
+        txt = raw.decode("ascii")
+        ids = [txt[a:b] for a, b in zip(bounds[:-1], bounds[1:])]
+    else:
+        ids = [raw[a:b].decode("utf-8", "replace") for a, b in zip(bounds[:-1], bounds[1:])]
     return ids, residues, offsets
 
 
