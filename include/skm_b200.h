@@ -236,6 +236,14 @@ SKM_API int skm_count_csr_wide(const uint8_t *d_residues, int64_t nres, const in
                        uint64_t *d_codes_out, uint32_t *d_cols_out, int32_t *d_vals, void *workspace,
                        size_t workspace_bytes, skm_stream_t stream);
 
+/* The same fan-in when the input is a concatenation of n_runs SORTED runs (what a rank receives from the all_to_all of
+ * the sparse learn exchange): pairwise merge tree + reduce-by-key, ceil(log2 n_runs) + 1 streaming passes instead of a
+ * radix sort.  run_offsets_host: HOST array [n_runs + 1] of entry offsets into d_keys_in / d_vals_in. */
+SKM_API size_t skm_coo_merge_runs_workspace(int64_t n, int n_runs);
+SKM_API int skm_coo_merge_runs(const uint64_t *d_keys_in, const int64_t *d_vals_in, const int64_t *run_offsets_host,
+                       int n_runs, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
+                       void *workspace, size_t workspace_bytes, skm_stream_t stream);
+
 /* Annotation-major COO (key = ann * S + code) -> k-mer-major CSC for the SpMM:
  * d_colptr int64 [S+1], d_rows int32 [nnz] (annotation), d_mvals int32 [nnz] = M[a, c],
  * d_mnorm2 (nullable) = ||m_a||^2 (exact integer sum, as float64), d_inv_m32 (nullable) =

@@ -19,6 +19,8 @@
 //                     then scan the accumulators for the top-2 (float32 screening, exact float64
 //                     scores for the survivors; apply.smk:278-335).
 //  window_keys_kernel is also the key generator of skm_count_csr (skm_count.cu).
+#include <vector>
+
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
@@ -492,6 +494,78 @@ int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n
     SKM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, d_keys_in, sk, d_vals_in, sv, n, 0, end_bit, st));
     temp_bytes = workspace_bytes - size_t((char *)temp - (char *)workspace);
     SKM_CUDA_TRY(cub::DeviceReduce::ReduceByKey(temp, temp_bytes, sk, d_keys_out, sv, d_vals_out, d_n_out, cub::Sum(), n, st));
+    return SKM_OK;
+}
+
+// ---- merge of SORTED runs (the fan-in after the all_to_all: W runs, one per sending rank) ----------------------
+// Pairwise merge tree (cub::DeviceMerge, ceil(log2 W) rounds of one streaming pass each) + reduce-by-key, instead of
+// a radix sort over the key bits (5 passes for the C3 matrix).
+size_t skm_coo_merge_runs_workspace(int64_t n, int n_runs) {
+    using namespace skm;
+    if (n <= 0 || n_runs <= 0) return 256;
+    size_t t_m = 0, t_red = 0;
+    const int half = (int)std::min<int64_t>(n, (1ll << 31) - 1);
+    cub::DeviceMerge::MergePairs(nullptr, t_m, (const uint64_t *)nullptr, (const int64_t *)nullptr, half, (const uint64_t *)nullptr,
+                                 (const int64_t *)nullptr, half, (uint64_t *)nullptr, (int64_t *)nullptr);
+    cub::DeviceReduce::ReduceByKey(nullptr, t_red, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int64_t *)nullptr,
+                                   (int64_t *)nullptr, (int64_t *)nullptr, cub::Sum(), n);
+    return 4 * al(size_t(n) * 8) + al(std::max(t_m, t_red)) + 1024;
+}
+
+int skm_coo_merge_runs(const uint64_t *d_keys_in, const int64_t *d_vals_in, const int64_t *run_offsets_host, int n_runs,
+                       uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out, void *workspace, size_t workspace_bytes,
+                       skm_stream_t stream) {
+    using namespace skm;
+    if (n_runs < 0 || !d_n_out || (n_runs > 0 && !run_offsets_host)) { set_error("skm_coo_merge_runs: bad arguments"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, 8, st));
+    if (n_runs == 0) return SKM_OK;
+    const int64_t base0 = run_offsets_host[0], n = run_offsets_host[n_runs] - base0;
+    for (int r = 0; r < n_runs; ++r)
+        if (run_offsets_host[r + 1] < run_offsets_host[r]) { set_error("skm_coo_merge_runs: run offsets must not decrease"); return SKM_ERR_INVALID; }
+    if (n == 0) return SKM_OK;
+    if (n >= (1ll << 31)) { set_error("skm_coo_merge_runs: more than 2^31 entries"); return SKM_ERR_UNSUPPORTED; }
+    if (!d_keys_in || !d_vals_in || !d_keys_out || !d_vals_out) { set_error("skm_coo_merge_runs: NULL argument"); return SKM_ERR_INVALID; }
+    const size_t need = skm_coo_merge_runs_workspace(n, n_runs);
+    if (!workspace || workspace_bytes < need) { set_error("skm_coo_merge_runs: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const size_t seg = al(size_t(n) * 8);
+    uint64_t *kb[2] = {(uint64_t *)p, (uint64_t *)(p + seg)};
+    int64_t *vb[2] = {(int64_t *)(p + 2 * seg), (int64_t *)(p + 3 * seg)};
+    void *temp = p + 4 * seg;
+    const size_t temp_cap = workspace_bytes - size_t((char *)temp - (char *)workspace);
+    // run boundaries relative to the first run
+    std::vector<int64_t> cur(n_runs + 1);
+    for (int r = 0; r <= n_runs; ++r) cur[r] = run_offsets_host[r] - base0;
+    const uint64_t *src_k = d_keys_in + base0;
+    const int64_t *src_v = d_vals_in + base0;
+    int flip = 0;
+    while (cur.size() > 2) {
+        std::vector<int64_t> next;
+        next.push_back(0);
+        uint64_t *dk = kb[flip];
+        int64_t *dv = vb[flip];
+        const int runs = int(cur.size()) - 1;
+        for (int r = 0; r < runs; r += 2) {
+            const int64_t a0 = cur[r], a1 = cur[r + 1];
+            if (r + 1 < runs) {
+                const int64_t b1 = cur[r + 2];
+                size_t tb = temp_cap;
+                SKM_CUDA_TRY(cub::DeviceMerge::MergePairs(temp, tb, src_k + a0, src_v + a0, (int)(a1 - a0), src_k + a1, src_v + a1, (int)(b1 - a1),
+                                                          dk + a0, dv + a0, ::cuda::std::less<>{}, st));
+                next.push_back(b1);
+            } else {                                    // odd run out: carried over unchanged
+                SKM_CUDA_TRY(cudaMemcpyAsync(dk + a0, src_k + a0, size_t(a1 - a0) * 8, cudaMemcpyDeviceToDevice, st));
+                SKM_CUDA_TRY(cudaMemcpyAsync(dv + a0, src_v + a0, size_t(a1 - a0) * 8, cudaMemcpyDeviceToDevice, st));
+                next.push_back(a1);
+            }
+        }
+        cur.swap(next);
+        src_k = dk; src_v = dv;
+        flip ^= 1;
+    }
+    size_t tb = temp_cap;
+    SKM_CUDA_TRY(cub::DeviceReduce::ReduceByKey(temp, tb, src_k, d_keys_out, src_v, d_vals_out, d_n_out, cub::Sum(), n, st));
     return SKM_OK;
 }
 

@@ -156,14 +156,15 @@ def allgather_tables(*columns: torch.Tensor) -> Tuple[torch.Tensor, ...]:
     return tuple(out)
 
 
-def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Sequence[int], return_runs: bool = False):
     """Sparse learn fan-in (learn.smk:467-494 for COO matrices): rank r receives from every rank the
     entries whose key lies in [key_bounds[r], key_bounds[r+1]).  `keys` must be sorted (int64 holding
     non-negative keys), so each destination is one contiguous run.  The received runs still have to be
-    merged (engine.coo_merge).  key_bounds has world+1 entries."""
+    merged (engine.coo_merge / coo_merge_runs).  key_bounds has world+1 entries.  return_runs: also return the
+    sizes of the W received runs (each sorted), in rank order."""
     rank, w = world()
     if w == 1:
-        return keys, vals
+        return (keys, vals, [keys.numel()]) if return_runs else (keys, vals)
     b = torch.tensor(list(key_bounds), dtype=torch.int64, device=keys.device)
     cut = torch.searchsorted(keys, b)
     send = (cut[1:] - cut[:-1]).contiguous()
@@ -175,7 +176,7 @@ def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds
     out_v = torch.empty(sum(recv_l), dtype=vals.dtype, device=vals.device)
     dist.all_to_all_single(out_k, keys[lo:hi].contiguous(), recv_l, send_l)
     dist.all_to_all_single(out_v, vals[lo:hi].contiguous(), recv_l, send_l)
-    return out_k, out_v
+    return (out_k, out_v, recv_l) if return_runs else (out_k, out_v)
 
 
 def balanced_annotation_bounds(keys: torch.Tensor, S: int, n_ann: int) -> List[int]:

@@ -682,6 +682,25 @@ def gather_sequences(batch: SequenceBatch, sel: torch.Tensor) -> Tuple[torch.Ten
     return out_res, out_off
 
 
+def coo_merge_runs(keys: torch.Tensor, vals: torch.Tensor, run_sizes: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """coo_merge for an input that is a concatenation of SORTED runs (run_sizes entries each): merge tree + reduce-by-key."""
+    dev = _require_cuda(keys.device)
+    n = keys.numel()
+    assert sum(run_sizes) == n
+    keys, vals = keys.contiguous(), vals.contiguous()
+    offs = np.zeros(len(run_sizes) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(run_sizes, dtype=np.int64), out=offs[1:])
+    ws_bytes = lib().skm_coo_merge_runs_workspace(n, len(run_sizes))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    ov = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    dn = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_coo_merge_runs(_ptr(keys), _ptr(vals), offs.ctypes.data, len(run_sizes), _ptr(ok), _ptr(ov), _ptr(dn), _ptr(ws),
+                                   ws_bytes, _stream()))
+    m = int(dn.item())
+    return ok[:m].clone(), ov[:m].clone()
+
+
 def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int,
                  max_chunk_res: int = 1 << 28, method: str = "grouped") -> Tuple[torch.Tensor, torch.Tensor]:
     """Annotation x k-mer count matrix as a COO list sorted by key = ann * S + code
@@ -1130,6 +1149,6 @@ def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n
         ann_bounds = D.balanced_annotation_bounds(keys, S, n_ann)
     else:
         ann_bounds = [n_ann * r // w for r in range(w)] + [n_ann]
-    k2, v2 = D.alltoall_coo_by_key_range(keys, vals, [a * int(S) for a in ann_bounds])
-    k3, v3 = coo_merge(k2, v2, key_bound=n_ann * S)
+    k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, [a * int(S) for a in ann_bounds], return_runs=True)
+    k3, v3 = coo_merge_runs(k2, v2, runs)           # W sorted runs, one per sender: merge tree + reduce-by-key
     return k3, v3, (ann_bounds[rank], ann_bounds[rank + 1])

@@ -400,3 +400,24 @@ def test_kmer_totals_counts_only(a, k):
     assert torch.equal(E.kmer_totals(batch, a, k), count)
     _, (si, pos, code, valid), _ = _codes_oracle(seqs, a, k)
     assert np.array_equal(count.cpu().numpy(), np.bincount(code[valid].astype(np.int64), minlength=tab.nsym ** k))
+
+
+@pytest.mark.parametrize("nruns", [1, 2, 3, 4, 7, 8])
+def test_coo_merge_runs_equals_sort_merge(nruns):
+    """Merge tree over sorted runs (the multi-GPU fan-in) == sort + reduce-by-key, including empty runs."""
+    rng = np.random.default_rng(nruns)
+    runs_k, runs_v, sizes = [], [], []
+    for r in range(nruns):
+        n = 0 if (r == 2 and nruns > 3) else int(rng.integers(1, 5000))
+        k = np.unique(rng.integers(0, 20000, size=n)).astype(np.int64)           # sorted, distinct inside a run
+        runs_k.append(k)
+        runs_v.append(rng.integers(1, 100, size=len(k)).astype(np.int64))
+        sizes.append(len(k))
+    keys = torch.from_numpy(np.concatenate(runs_k)).cuda()
+    vals = torch.from_numpy(np.concatenate(runs_v)).cuda()
+    k1, v1 = E.coo_merge(keys, vals, key_bound=20000)
+    k2, v2 = E.coo_merge_runs(keys, vals, sizes)
+    assert torch.equal(k1, k2) and torch.equal(v1, v2)
+    want = np.zeros(20000, np.int64)
+    np.add.at(want, keys.cpu().numpy(), vals.cpu().numpy())
+    assert np.array_equal(k2.cpu().numpy(), np.flatnonzero(want)) and np.array_equal(v2.cpu().numpy(), want[want > 0])
