@@ -399,6 +399,27 @@ def read_confidence_csv(path: str) -> Dict[float, float]:
     return dict(zip(t.iloc[:, 0].astype(float).tolist(), t.iloc[:, 1].astype(float).tolist()))
 
 
+def delta_and_confidence(r: E.ApplyResult, conf: Dict[float, float], n_ann: int) -> Tuple[np.ndarray, np.ndarray]:
+    """delta = round(top1 - top2, 2) and Confidence = lookup of delta (apply.smk:312-335) for all queries at once:
+    the Difference bin of every query comes from the device (skm_confidence_hist without histograms, numpy's
+    rint(x * 100) / 100), delta and the confidence are table look-ups over the 101 values.  Rows whose bin is
+    undefined (a single annotation: no runner-up) fall back to the scalar formula."""
+    from . import confidence as CF
+
+    bins = CF.difference_bins(r.top1, r.score1, r.score2, n_ann).cpu().numpy()
+    vals = np.array(CF.POSSIBLE_VALS + [np.nan], dtype=np.float64)
+    table = np.array([conf.get(v, np.nan) for v in CF.POSSIBLE_VALS] + [np.nan], dtype=np.float64)
+    idx = np.where(bins == 255, len(CF.POSSIBLE_VALS), bins).astype(np.int64)
+    delta, confidence = vals[idx], table[idx]
+    odd = np.flatnonzero(bins == 255)
+    if odd.size:
+        d = np.round(r.score1[torch.from_numpy(odd).to(r.score1.device)].cpu().numpy()
+                     - r.score2[torch.from_numpy(odd).to(r.score2.device)].cpu().numpy(), 2)
+        delta[odd] = d
+        confidence[odd] = [conf.get(float(x), np.nan) for x in d]
+    return delta, confidence
+
+
 def apply_rule(npz: str, counts_csv: str, confidence_csv: str, out_summary: str, out_scores: Optional[str] = None,
                save_associations: bool = False) -> ScoreResult:
     """apply.smk:147-353: Prediction = best annotation, Score = its cosine,
@@ -417,9 +438,8 @@ def apply_rule(npz: str, counts_csv: str, confidence_csv: str, out_summary: str,
         cols: Dict[str, object] = {a: S[:, j] for j, a in enumerate(anns)}
         cols[INDEX_COL] = ids
         _write_arrow_csv(out_scores, cols)
-    delta = np.round(s1 - s2, 2)
     conf = read_confidence_csv(confidence_csv)
-    confidence = np.array([conf.get(float(d), np.nan) for d in delta], dtype=np.float64)
+    delta, confidence = delta_and_confidence(r, conf, len(anns))
     import pyarrow as pa
 
     _write_arrow_csv(out_summary, {

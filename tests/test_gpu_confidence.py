@@ -122,3 +122,24 @@ def test_evaluate_results_equals_evaluate_rule(tmp_path):
     R.evaluate_results(results, str(tmp_path / "c2.csv"), str(tmp_path / "g2.csv"))
     assert (tmp_path / "g1.csv").read_bytes() == (tmp_path / "g2.csv").read_bytes() == bytes(D["two_glob"])
     assert (tmp_path / "c1.csv").read_bytes() == (tmp_path / "c2.csv").read_bytes() == bytes(D["two_conf"])
+
+
+def test_delta_and_confidence_vectorised_equals_scalar():
+    """apply.smk:312-335 for all queries at once (device bins + table look-up) == np.round + dict.get per row,
+    including rows without a runner-up (one annotation) and a confidence file with missing keys."""
+    from snekmer_b200 import rules as R
+
+    rng = np.random.default_rng(12)
+    q = 5000
+    s1 = np.round(rng.random(q), 4)
+    s2 = np.round(s1 * rng.random(q), 4)
+    s2[::7] = s1[::7]                                   # exact ties
+    s2[::11] = np.nan                                   # no runner-up
+    conf = {v: 0.5 + 0.004 * i for i, v in enumerate(CF.POSSIBLE_VALS) if i % 13 != 5}       # some keys missing
+    r = E.ApplyResult(torch.zeros(q, dtype=torch.int32, device="cuda"), torch.ones(q, dtype=torch.int32, device="cuda"),
+                      torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda())
+    delta, confidence = R.delta_and_confidence(r, conf, 3)
+    want_delta = np.round(s1 - s2, 2)
+    want_conf = np.array([conf.get(float(d), np.nan) for d in want_delta])
+    assert np.array_equal(delta, want_delta, equal_nan=True)
+    assert np.array_equal(confidence, want_conf, equal_nan=True)
