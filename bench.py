@@ -299,8 +299,7 @@ def run_learn(ctx, args):
     state = {}
 
     def step(timed):
-        count = E.kmer_totals(batch, alphabet, k)                    # Totals row: occurrence counts over ALL sequences
-        keys, vals = E.learn_sparse(batch, alphabet, k, d_ann, n_ann)
+        keys, vals, count = E.learn_sparse_with_totals(batch, alphabet, k, d_ann, n_ann)     # matrix + Totals row over ALL sequences
         if ctx.world > 1:
             keys, vals, _ = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
             ctx.dist.all_reduce(count)

@@ -236,6 +236,11 @@ SKM_API int skm_count_csr_wide(const uint8_t *d_residues, int64_t nres, const in
                        uint64_t *d_codes_out, uint32_t *d_cols_out, int32_t *d_vals, void *workspace,
                        size_t workspace_bytes, skm_stream_t stream);
 
+/* Column sums of a COO matrix: d_totals[key % S] += value (d_totals int64 [S], accumulated, not cleared): the annotated
+ * share of the Totals row (learn.smk:380) from the already aggregated matrix, one atomic per entry. */
+SKM_API int skm_coo_colsum(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, int64_t S,
+                   int64_t *d_totals, skm_stream_t stream);
+
 /* The same fan-in when the input is a concatenation of n_runs SORTED runs (what a rank receives from the all_to_all of
  * the sparse learn exchange): pairwise merge tree + reduce-by-key, ceil(log2 n_runs) + 1 streaming passes instead of a
  * radix sort.  run_offsets_host: HOST array [n_runs + 1] of entry offsets into d_keys_in / d_vals_in. */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "skm_gather_sequences": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "skm_coo_merge_workspace": (_sz, [_i64]),
     "skm_coo_merge": (_int, [_p, _p, _i64, _u64, _p, _p, _p, _p, _sz, _p]),
+    "skm_coo_colsum": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "skm_coo_merge_runs_workspace": (_sz, [_i64, _int]),
     "skm_coo_merge_runs": (_int, [_p, _p, _p, _int, _p, _p, _p, _p, _sz, _p]),
     "skm_csc_build_workspace": (_sz, [_i64, _i64]),

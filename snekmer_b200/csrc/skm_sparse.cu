@@ -497,6 +497,30 @@ int skm_coo_merge(const uint64_t *d_keys_in, const int64_t *d_vals_in, int64_t n
     return SKM_OK;
 }
 
+// ---- Totals from the matrix -----------------------------------------------------------------------------------
+// totals[code] += sum over annotations of M[ann, code]: the column sums of a COO list.  The learn step needs the
+// k-mer totals over ALL sequences (learn.smk:380); the annotated part is already aggregated per (annotation, k-mer) in
+// the matrix — one atomic per ENTRY instead of one per window — and only the unannotated sequences are still
+// counted window by window (skm_basis_accumulate with d_first = NULL).
+namespace skm {
+__global__ void __launch_bounds__(256) coo_colsum_kernel(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals, int64_t nnz,
+                                                         uint64_t S, unsigned long long *__restrict__ totals) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x)
+        atomicAdd(totals + keys[i] % S, (unsigned long long)vals[i]);
+}
+}  // namespace skm
+
+int skm_coo_colsum(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, int64_t S, int64_t *d_totals, skm_stream_t stream) {
+    using namespace skm;
+    if (nnz < 0 || S <= 0) { set_error("skm_coo_colsum: bad sizes"); return SKM_ERR_INVALID; }
+    if (nnz == 0) return SKM_OK;
+    if (!d_keys || !d_vals || !d_totals) { set_error("skm_coo_colsum: NULL argument"); return SKM_ERR_INVALID; }
+    const int grid = (int)std::min<int64_t>((nnz + 255) / 256, int64_t(sm_count()) * 16);
+    coo_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_vals, nnz, (uint64_t)S, reinterpret_cast<unsigned long long *>(d_totals));
+    SKM_LAUNCH_CHECK("coo_colsum_kernel");
+    return SKM_OK;
+}
+
 // ---- merge of SORTED runs (the fan-in after the all_to_all: W runs, one per sending rank) ----------------------
 // Pairwise merge tree (cub::DeviceMerge, ceil(log2 W) rounds of one streaming pass each) + reduce-by-key, instead of
 // a radix sort over the key bits (5 passes for the C3 matrix).

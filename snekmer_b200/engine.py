@@ -775,6 +775,28 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
     return coo_merge(torch.cat(parts_k), torch.cat(parts_v), key_bound=n_ann * S)
 
 
+def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int):
+    """learn_sparse + the Totals row (k-mer occurrences over ALL sequences, learn.smk:380) -> (keys, vals, totals int64 [S]).
+    The annotated share of the totals is the column sums of the matrix (one atomic per entry instead of one per
+    window); only the unannotated sequences are counted window by window."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    S = code_space(tab.nsym, k)
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    keys, vals = learn_sparse(batch, alphabet, k, ann_id, n_ann)
+    totals = torch.zeros(S, dtype=torch.int64, device=dev)
+    check(lib().skm_coo_colsum(_ptr(keys), _ptr(vals), keys.numel(), S, _ptr(totals), _stream()))
+    rest = torch.nonzero((ann_id < 0) | (ann_id >= n_ann)).reshape(-1)
+    if rest.numel():
+        g_res, g_off = gather_sequences(batch, rest)
+        off_host = g_off.cpu().numpy()
+        sub = SequenceBatch(g_res, g_off, off_host)
+        basis_accumulate(sub, alphabet, k, totals, None, 0)
+    return keys, vals, totals
+
+
 @dataclass
 class AnnotationCSC:
     """k-mer-major view of an annotation slice [ann_lo, ann_lo + n_ann) of a learned matrix."""

@@ -421,3 +421,21 @@ def test_coo_merge_runs_equals_sort_merge(nruns):
     want = np.zeros(20000, np.int64)
     np.add.at(want, keys.cpu().numpy(), vals.cpu().numpy())
     assert np.array_equal(k2.cpu().numpy(), np.flatnonzero(want)) and np.array_equal(v2.cpu().numpy(), want[want > 0])
+
+
+@pytest.mark.parametrize("a,k", [(5, 3), (2, 8), (None, 4)])
+def test_learn_sparse_with_totals(a, k):
+    """Totals from the matrix's column sums + the unannotated sequences == the occurrence table over all sequences."""
+    rng = np.random.default_rng(k + 31)
+    seqs = _rand_seqs(rng, 1500, 0, 300)
+    batch = E.SequenceBatch.from_strings(seqs)
+    n_ann = 17
+    ann = rng.integers(-1, n_ann + 2, size=len(seqs)).astype(np.int32)       # -1 and ids >= n_ann are both "unannotated"
+    keys, vals, totals = E.learn_sparse_with_totals(batch, a, k, torch.from_numpy(ann), n_ann)
+    assert torch.equal(totals, E.kmer_totals(batch, a, k))
+    k2, v2 = E.learn_sparse(batch, a, k, torch.from_numpy(ann), n_ann, method="global")
+    assert torch.equal(keys, k2) and torch.equal(vals, v2)
+    # all sequences annotated / none annotated
+    _, _, t_all = E.learn_sparse_with_totals(batch, a, k, torch.zeros(len(seqs), dtype=torch.int32), n_ann)
+    _, _, t_none = E.learn_sparse_with_totals(batch, a, k, torch.full((len(seqs),), -1, dtype=torch.int32), n_ann)
+    assert torch.equal(t_all, totals) and torch.equal(t_none, totals)
