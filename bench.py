@@ -155,8 +155,6 @@ class Ctx:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"          # keeps NCCL's version banner off stdout (one JSON line)
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -630,15 +628,35 @@ def reference_arm(args):
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
     cb = dict(vals[-1], value=v)
-    print(json.dumps({"impl": "reference", "metric": "sequences/sec vectorize", "value": v, "unit": "sequences/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                      "cpu_baseline": cb,
-                      "e2e": {"value": v, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    _emit({"impl": "reference", "metric": "sequences/sec vectorize", "value": v, "unit": "sequences/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Everything any library writes to fd 1 (NCCL's version banner, torchrun notices) goes to stderr; the ONE JSON line
+    is written to the real stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -665,7 +683,7 @@ def main():
         if not args.no_cpu and ctx.world == 1 and cpu is not None:
             ncores = os.cpu_count() or 1
             line["cpu_baseline"] = cpu(args.cpu_sample or 20000 * min(ncores, 64))
-        print(json.dumps(line))
+        _emit(line)
     ctx.finish()
 
 
