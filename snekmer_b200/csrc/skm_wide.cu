@@ -304,19 +304,30 @@ int skm_basis_sorted_finalize(const uint64_t *d_codes, const int64_t *d_counts, 
         codes_m = keys_b; counts_m = v3; first_m = v1;       // free now: keys_a, v2, idx_a, idx_b
     }
     // ---- 2. min_filter: keep count > min_filter (kmerize.smk:97-104) ----
-    keep_flags_kernel<<<grid, 256, 0, st>>>(counts_m, d_m, n, min_filter, flags);
-    SKM_LAUNCH_CHECK("keep_flags_kernel");
-    int64_t *cnt_sel = v2, *first_sel = reinterpret_cast<int64_t *>(keys_a);
-    int64_t *d_tmpK = reinterpret_cast<int64_t *>(idx_a);    // two throw-away selection counts
-    temp_bytes = temp_cap;
-    SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, counts_m, flags, cnt_sel, d_tmpK, n, st));
-    temp_bytes = temp_cap;
-    SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, first_m, flags, first_sel, d_tmpK, n, st));
-    temp_bytes = temp_cap;
-    SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, codes_m, flags, d_sorted_codes_out, d_K_out, n, st));   // d_m dead from here
-    // ---- 3. first-occurrence order: sort the kept entries by first position (padding sorts last) ----
-    pad_i64_kernel<<<grid, 256, 0, st>>>(first_sel, d_K_out, n, INT64_MAX);
-    SKM_LAUNCH_CHECK("pad_i64_kernel");
+    const int64_t *cnt_sel, *first_sel;
+    if (merged && min_filter <= 0) {
+        // one merged table and nothing to filter (every entry occurs at least once): K = n, no selection passes
+        cnt_sel = counts_m;
+        first_sel = first_m;
+        SKM_CUDA_TRY(cudaMemcpyAsync(d_sorted_codes_out, codes_m, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+        keep_flags_kernel<<<grid, 256, 0, st>>>(counts_m, d_m, n, min_filter, flags);
+        SKM_LAUNCH_CHECK("keep_flags_kernel");
+        int64_t *cnt_w = v2, *first_w = reinterpret_cast<int64_t *>(keys_a);
+        int64_t *d_tmpK = reinterpret_cast<int64_t *>(idx_a);    // two throw-away selection counts
+        temp_bytes = temp_cap;
+        SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, counts_m, flags, cnt_w, d_tmpK, n, st));
+        temp_bytes = temp_cap;
+        SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, first_m, flags, first_w, d_tmpK, n, st));
+        temp_bytes = temp_cap;
+        SKM_CUDA_TRY(cub::DeviceSelect::Flagged(temp, temp_bytes, codes_m, flags, d_sorted_codes_out, d_K_out, n, st));   // d_m dead from here
+        // padding behind the K kept entries sorts last in step 3
+        pad_i64_kernel<<<grid, 256, 0, st>>>(first_w, d_K_out, n, INT64_MAX);
+        SKM_LAUNCH_CHECK("pad_i64_kernel");
+        cnt_sel = cnt_w;
+        first_sel = first_w;
+    }
+    // ---- 3. first-occurrence order: sort the kept entries by first position ----
     iota_u32_kernel<<<grid, 256, 0, st>>>(idx_a, n);
     SKM_LAUNCH_CHECK("iota_u32_kernel");
     temp_bytes = temp_cap;
