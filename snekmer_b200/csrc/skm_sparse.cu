@@ -183,6 +183,8 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
     __shared__ int64_t s_p0[SPA_EB];
     __shared__ int s_len[SPA_EB];
     __shared__ uint32_t s_cnt[SPA_EB];
+    __shared__ int s_first[SPA_EB + 1];                 // segments of the block's entries before entry j (exclusive prefix)
+    __shared__ int s_wtot[SPA_THREADS / 32];
     AccT *acc = reinterpret_cast<AccT *>(s_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = SPA_THREADS / 32;
@@ -193,31 +195,56 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
     __syncthreads();
     for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
         const int64_t e0 = __ldg(rowptr + q), e1 = __ldg(rowptr + q + 1);
-        // ---- walk: blocks of SPA_EB query entries are staged in shared memory; every column is cut into segments of
-        // SPA_SEG entries and segment s of entry j goes to warp (j + s) mod NW, so that long columns (popular k-mers
+        // ---- blocks of SPA_EB query entries are staged in shared memory; every column is cut into segments of SPA_SEG
+        // entries, the (entry, segment) items are dealt round-robin to the warps, so that long columns (popular k-mers
         // meet thousands of annotations) spread over the CTA.  A lane loads its SPA_SEG / 32 entries of the segment
         // before the first atomic: the loads of a segment are all in flight together. ----
         unsigned long long n2 = 0;
         for (int64_t b0 = e0; b0 < e1; b0 += SPA_EB) {
             const int nb = (e1 - b0 < SPA_EB) ? int(e1 - b0) : SPA_EB;
-            for (int j = tid; j < nb; j += SPA_THREADS) {
-                const uint32_t c = __ldg(qcols + b0 + j);
-                const uint32_t cnt = uint32_t(__ldg(qvals + b0 + j));
+            // stage entry tid (nb <= SPA_EB <= SPA_THREADS) and scan the entries' segment counts: the block's work is the
+            // list of (entry, segment) items, item t = s_first[j] + s
+            int nseg = 0;
+            if (tid < nb) {
+                const uint32_t c = __ldg(qcols + b0 + tid);
+                const uint32_t cnt = uint32_t(__ldg(qvals + b0 + tid));
                 const int64_t p0 = __ldg(colptr + c);
-                s_p0[j] = p0;
-                s_len[j] = int(__ldg(colptr + c + 1) - p0);
-                s_cnt[j] = cnt;
+                const int len = int(__ldg(colptr + c + 1) - p0);
+                s_p0[tid] = p0;
+                s_len[tid] = len;
+                s_cnt[tid] = cnt;
                 n2 += (unsigned long long)cnt * cnt;
+                nseg = (len + SPA_SEG - 1) / SPA_SEG;
             }
+            int incl = nseg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_wtot[warp] = incl;
             __syncthreads();
-            for (int j = 0; j < nb; ++j) {
-                const int len = s_len[j];
-                int seg = (warp - j) & (NW - 1);
-                if (seg * SPA_SEG >= len) continue;
-                const AccT cnt = AccT(s_cnt[j]);
-                const int64_t p0 = s_p0[j];
-                for (; seg * SPA_SEG < len; seg += NW) {
-                    const int64_t pb = p0 + int64_t(seg) * SPA_SEG;
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_wtot[w];
+            if (tid <= nb) s_first[tid] = before + incl - nseg;          // tid == nb: the total
+            __syncthreads();
+            const int n_items = s_first[nb];
+            // ---- walk: item t goes to warp t mod NW; a lane first finds (entry, segment) of one of its warp's next 32
+            // items by binary search in s_first, then the warp processes them one after the other.  (The first version
+            // let every warp loop over ALL entries and skip those without a segment for it: 85 % of 541 M loop trips did
+            // nothing — 23 % of the kernel's samples — and the warps finished unevenly: 15 % barrier stalls.) ----
+            for (int base = warp; base < n_items; base += 32 * NW) {
+                const int t = base + lane * NW;
+                int ej = 0, es = 0;
+                if (t < n_items) {
+                    int lo = 0, hi = nb;                            // last j with s_first[j] <= t
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_first[mid] <= t) lo = mid; else hi = mid; }
+                    ej = lo;
+                    es = t - s_first[lo];
+                }
+                const int in_round = min(32, (n_items - base + NW - 1) / NW);
+                for (int i = 0; i < in_round; ++i) {
+                    const int j = __shfl_sync(FULL, ej, i), seg = __shfl_sync(FULL, es, i);
+                    const int len = s_len[j];
+                    const AccT cnt = AccT(s_cnt[j]);
+                    const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
                     const int n = min(SPA_SEG, len - seg * SPA_SEG);
                     int r[SPA_SEG / 32];
                     uint32_t m[SPA_SEG / 32];
