@@ -266,7 +266,7 @@ SKM_API int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t
  * max(M) * (largest row total of the queries) < 2^32, else 64); scores are
  * dot * (1/||q||) * (1/||m||) in float64 like skm_apply_dense, ties -> lowest index.
  * n_ann <= 51200 (32-bit) or 25600 (64-bit) per call: shard the annotations and merge with
- * skm_top2_merge.  d_qnorm2 (nullable) receives ||q||^2. */
+ * skm_top2_merge.  d_qnorm2 (nullable) receives ||q||^2.  d_inv_m32 must be 16-byte aligned. */
 SKM_API int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int32_t *d_vals,
                      int64_t nq, const int64_t *d_colptr, const int32_t *d_rows,
                      const int32_t *d_mvals, const double *d_mnorm2, const float *d_inv_m32,

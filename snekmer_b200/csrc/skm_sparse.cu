@@ -273,6 +273,16 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
         float thr = 1e-30f;                                    // > 0: zero dots are never candidates (see the final fill)
         for (int a0 = tid * PER; a0 < n_pad; a0 += SPA_THREADS * PER) {
             AccT v[PER];
+            // the screening factors are loaded up front (one coalesced vector, independent of the accumulators): loaded
+            // per non-zero accumulator they put an L2 round trip in front of every multiply
+            float inv[PER];
+            if (a0 + PER <= n_ann) {
+                if (PER == 4) *reinterpret_cast<float4 *>(inv) = __ldg(reinterpret_cast<const float4 *>(inv_m32 + a0));
+                else *reinterpret_cast<float2 *>(inv) = __ldg(reinterpret_cast<const float2 *>(inv_m32 + a0));
+            } else {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) inv[i] = (a0 + i < n_ann) ? __ldg(inv_m32 + a0 + i) : 0.f;
+            }
             *reinterpret_cast<uint4 *>(v) = *reinterpret_cast<const uint4 *>(&acc[a0]);
             bool any = false;
 #pragma unroll
@@ -282,7 +292,7 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
 #pragma unroll
                 for (int i = 0; i < PER; ++i) {
                     if (v[i] != 0) {
-                        const float f = float(v[i]) * __ldg(inv_m32 + a0 + i);
+                        const float f = float(v[i]) * inv[i];
                         if (f >= thr) {
                             top2x_push(bx, f, (unsigned long long)v[i], a0 + i, inv_qn, mnorm2);
                             if (bx.i2 >= 0) thr = fmaxf(thr, bx.f2 * 0.99999f);
@@ -681,6 +691,7 @@ int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int3
     if (nq < 0 || n_ann <= 0 || n_ann > cap) { set_error("skm_apply_sparse: n_ann=%lld outside [1, %lld] for %d-bit accumulators (shard the annotations)", (long long)n_ann, (long long)cap, acc_bits); return n_ann > cap ? SKM_ERR_UNSUPPORTED : SKM_ERR_INVALID; }
     if (nq == 0) return SKM_OK;
     if (!d_rowptr || !d_colptr || !d_mnorm2 || !d_inv_m32 || !d_top1 || !d_top2 || !d_score1 || !d_score2) { set_error("skm_apply_sparse: NULL argument"); return SKM_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(d_inv_m32) & 15u) != 0) { set_error("skm_apply_sparse: d_inv_m32 must be 16-byte aligned (vector loads)"); return SKM_ERR_INVALID; }
     const size_t smem = std::max<size_t>(size_t(n_ann + 4) * (acc_bits / 8), 116 * 1024);   // > half an SM: one CTA per SM by construction
     const int grid = (int)std::min<int64_t>(nq, int64_t(sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
