@@ -504,7 +504,8 @@ def run_apply_sparse(ctx, args):
     total_ms, e2e_ms, k_ms = ctx.max_over_ranks([total_ms, e2e_ms, float(np.mean(kern_ms))])
     ms = total_ms / args.steps
     peak, peak_kind = peaks()
-    alg_bytes = 8 * macs + 8 * nnzq + 40 * batch.n          # gathered CSC entries (row + value), query entries, row pointers + results
+    entry_bytes = 4 if all(c.packed is not None for c in cscs) else 8      # packed CSC: annotation << 16 | value in one word
+    alg_bytes = entry_bytes * macs + 8 * nnzq + 40 * batch.n          # gathered CSC entries, query entries, row pointers + results
     line = {"metric": "sequences/sec apply (sparse)", "value": ctx.world * args.nseq / (ms * 1e-3), "unit": "sequences/s", "n_gpus": ctx.world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "uint32 exact dots, float64 scaling", "data": "synthetic",
@@ -516,7 +517,7 @@ def run_apply_sparse(ctx, args):
                          "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": k_ms, "useful_macs": macs, "gmacs_per_s": macs / (k_ms * 1e-3) / 1e9,
                          "traffic": TRAFFIC.get("apply_sparse_kernel"),
-                         "note": "bytes = the CSC entries the gather formulation touches (8 B per multiply-accumulate, served by L2 and HBM)"}}
+                         "note": f"bytes = the CSC entries the gather formulation touches ({entry_bytes} B per multiply-accumulate, served by L2 and HBM); the kernel is latency / shared-atomic bound, see DESIGN.md"}}
     if not args.no_e2e:
         line["e2e"] = {"value": ctx.world * args.nseq / (e2e_ms * 1e-3), "unit": "sequences/s", "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": nres + 8 * (batch.n + 1), "d2h_bytes_per_step": 20 * batch.n,

@@ -170,11 +170,12 @@ constexpr int SPA_SEG = 256;       // CSC entries per segment (8 per lane)
 //   scan   every thread owns the same accumulators for every query (4 adjacent ones per step): float32 screening
 //          score acc * inv_m32 against the thread's running runner-up, survivors inserted into a Top2x; the
 //          accumulators are zeroed on the way.  The threads' top-2 lists are then merged with exact float64 scores.
-template <typename AccT>
+template <typename AccT, bool PACKED>
 __global__ void __launch_bounds__(SPA_THREADS, 1)
 apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ qcols, const int32_t *__restrict__ qvals,
                     int64_t nq, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rows,
-                    const int32_t *__restrict__ mvals, const double *__restrict__ mnorm2, const float *__restrict__ inv_m32,
+                    const int32_t *__restrict__ mvals, const uint32_t *__restrict__ packed,
+                    const double *__restrict__ mnorm2, const float *__restrict__ inv_m32,
                     int n_ann, int32_t *__restrict__ top1, int32_t *__restrict__ top2, double *__restrict__ sc1,
                     double *__restrict__ sc2, double *__restrict__ qnorm2_out) {
     extern __shared__ __align__(16) uint8_t s_raw[];
@@ -240,6 +241,36 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
                     es = t - s_first[lo];
                 }
                 const int in_round = min(32, (n_items - base + NW - 1) / NW);
+                if (PACKED) {
+                    // one 32-bit word per CSC entry (annotation << 16 | value): half the loads and registers, which pays
+                    // for a software pipeline — the next item's 8 loads are issued before the current item's atomics
+                    // (22 % of the samples of the unpacked kernel wait on the loads of the item they are about to use)
+                    uint32_t cur[SPA_SEG / 32], nxt[SPA_SEG / 32];
+                    int j = __shfl_sync(FULL, ej, 0), seg = __shfl_sync(FULL, es, 0);
+                    {
+                        const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
+                        const int n = min(SPA_SEG, s_len[j] - seg * SPA_SEG);
+#pragma unroll
+                        for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; cur[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
+                    }
+                    for (int i = 0; i < in_round; ++i) {
+                        const AccT cnt = AccT(s_cnt[j]);
+                        if (i + 1 < in_round) {
+                            j = __shfl_sync(FULL, ej, i + 1);
+                            seg = __shfl_sync(FULL, es, i + 1);
+                            const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
+                            const int n = min(SPA_SEG, s_len[j] - seg * SPA_SEG);
+#pragma unroll
+                            for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; nxt[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < SPA_SEG / 32; ++u)
+                            if (cur[u] & 0xFFFFu) atomicAdd(&acc[cur[u] >> 16], cnt * AccT(cur[u] & 0xFFFFu));      // values are >= 1
+#pragma unroll
+                        for (int u = 0; u < SPA_SEG / 32; ++u) cur[u] = nxt[u];
+                    }
+                    continue;
+                }
                 for (int i = 0; i < in_round; ++i) {
                     const int j = __shfl_sync(FULL, ej, i), seg = __shfl_sync(FULL, es, i);
                     const int len = s_len[j];
@@ -325,6 +356,12 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256) csc_pack_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ mvals, int64_t nnz,
+                                                       uint32_t *__restrict__ packed) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x)
+        packed[i] = (uint32_t(rows[i]) << 16) | (uint32_t(mvals[i]) & 0xFFFFu);
 }
 
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
@@ -681,8 +718,18 @@ int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t nnz, in
     return SKM_OK;
 }
 
+int skm_csc_pack(const int32_t *d_rows, const int32_t *d_mvals, int64_t nnz, uint32_t *d_packed, skm_stream_t stream) {
+    using namespace skm;
+    if (nnz < 0) { set_error("skm_csc_pack: negative size"); return SKM_ERR_INVALID; }
+    if (nnz == 0) return SKM_OK;
+    if (!d_rows || !d_mvals || !d_packed) { set_error("skm_csc_pack: NULL argument"); return SKM_ERR_INVALID; }
+    csc_pack_kernel<<<(int)std::min<int64_t>((nnz + 255) / 256, int64_t(sm_count()) * 16), 256, 0, (cudaStream_t)stream>>>(d_rows, d_mvals, nnz, d_packed);
+    SKM_LAUNCH_CHECK("csc_pack_kernel");
+    return SKM_OK;
+}
+
 int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int32_t *d_vals, int64_t nq,
-                     const int64_t *d_colptr, const int32_t *d_rows, const int32_t *d_mvals, const double *d_mnorm2,
+                     const int64_t *d_colptr, const int32_t *d_rows, const int32_t *d_mvals, const uint32_t *d_packed, const double *d_mnorm2,
                      const float *d_inv_m32, int64_t n_ann, int acc_bits, int32_t *d_top1, int32_t *d_top2,
                      double *d_score1, double *d_score2, double *d_qnorm2, skm_stream_t stream) {
     using namespace skm;
@@ -691,19 +738,21 @@ int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int3
     if (nq < 0 || n_ann <= 0 || n_ann > cap) { set_error("skm_apply_sparse: n_ann=%lld outside [1, %lld] for %d-bit accumulators (shard the annotations)", (long long)n_ann, (long long)cap, acc_bits); return n_ann > cap ? SKM_ERR_UNSUPPORTED : SKM_ERR_INVALID; }
     if (nq == 0) return SKM_OK;
     if (!d_rowptr || !d_colptr || !d_mnorm2 || !d_inv_m32 || !d_top1 || !d_top2 || !d_score1 || !d_score2) { set_error("skm_apply_sparse: NULL argument"); return SKM_ERR_INVALID; }
+    if (d_packed && n_ann > 65536) { set_error("skm_apply_sparse: the packed CSC holds 16-bit annotation indices (n_ann <= 65536)"); return SKM_ERR_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_inv_m32) & 15u) != 0) { set_error("skm_apply_sparse: d_inv_m32 must be 16-byte aligned (vector loads)"); return SKM_ERR_INVALID; }
     const size_t smem = std::max<size_t>(size_t(n_ann + 4) * (acc_bits / 8), 116 * 1024);   // > half an SM: one CTA per SM by construction
     const int grid = (int)std::min<int64_t>(nq, int64_t(sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
-    if (acc_bits == 32) {
-        SKM_CUDA_TRY(cudaFuncSetAttribute(apply_sparse_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        apply_sparse_kernel<uint32_t><<<grid, SPA_THREADS, smem, st>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_mvals, d_mnorm2, d_inv_m32,
-                                                                         (int)n_ann, d_top1, d_top2, d_score1, d_score2, d_qnorm2);
-    } else {
-        SKM_CUDA_TRY(cudaFuncSetAttribute(apply_sparse_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        apply_sparse_kernel<unsigned long long><<<grid, SPA_THREADS, smem, st>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_mvals, d_mnorm2,
-                                                                                   d_inv_m32, (int)n_ann, d_top1, d_top2, d_score1, d_score2, d_qnorm2);
+#define SKM_LAUNCH_SPA(ACC, PK)                                                                                              \
+    {                                                                                                                        \
+        auto kern = apply_sparse_kernel<ACC, PK>;                                                                            \
+        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        kern<<<grid, SPA_THREADS, smem, st>>>(d_rowptr, d_cols, d_vals, nq, d_colptr, d_rows, d_mvals, d_packed, d_mnorm2,   \
+                                              d_inv_m32, (int)n_ann, d_top1, d_top2, d_score1, d_score2, d_qnorm2);          \
     }
+    if (acc_bits == 32) { if (d_packed) SKM_LAUNCH_SPA(uint32_t, true) else SKM_LAUNCH_SPA(uint32_t, false) }
+    else { if (d_packed) SKM_LAUNCH_SPA(unsigned long long, true) else SKM_LAUNCH_SPA(unsigned long long, false) }
+#undef SKM_LAUNCH_SPA
     SKM_LAUNCH_CHECK("apply_sparse_kernel");
     return SKM_OK;
 }

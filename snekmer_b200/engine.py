@@ -809,10 +809,12 @@ class AnnotationCSC:
     n_ann: int
     ann_lo: int
     S: int
+    packed: Optional[torch.Tensor] = None   # int32 (uint32 pattern) [nnz]: row << 16 | value, when n_ann <= 65536 and max_m < 65536
 
 
-def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo: int = 0) -> AnnotationCSC:
-    """CSC of the annotation slice [ann_lo, ann_lo + n_ann) of a sorted COO matrix."""
+def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo: int = 0, pack: bool = True) -> AnnotationCSC:
+    """CSC of the annotation slice [ann_lo, ann_lo + n_ann) of a sorted COO matrix.  pack: also keep the entries as one
+    32-bit word each (annotation << 16 | value) when they fit — apply_sparse then reads half the bytes."""
     dev = _require_cuda(keys.device)
     if keys.numel():
         # the slice is contiguous because the list is sorted by ann * S + code
@@ -834,14 +836,18 @@ def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo
     mx = int(max_m.item())
     if mx >= 2 ** 31:
         raise SkmError(-3, f"csc_build: an annotation count of {mx} does not fit the 32-bit CSC values")
-    return AnnotationCSC(colptr, rows[:nnz], mvals[:nnz], mn2[:n_ann], inv32[:n_ann], mx, int(n_ann), int(ann_lo), int(S))
+    csc = AnnotationCSC(colptr, rows[:nnz], mvals[:nnz], mn2[:n_ann], inv32[:n_ann], mx, int(n_ann), int(ann_lo), int(S))
+    if pack and nnz and n_ann <= 65536 and mx < 65536:
+        csc.packed = torch.empty(nnz, dtype=torch.int32, device=dev)
+        check(lib().skm_csc_pack(_ptr(csc.rows), _ptr(csc.mvals), nnz, _ptr(csc.packed), _stream()))
+    return csc
 
 
 SPARSE_MAX_ANN = 50 * 1024          # annotations per apply_sparse call with 32-bit accumulators (half with 64-bit)
 
 
 def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, csc: AnnotationCSC,
-                 max_row_total: Optional[int] = None) -> ApplyResult:
+                 max_row_total: Optional[int] = None, use_packed: bool = True) -> ApplyResult:
     """SpMM scoring of CSR queries (codes + counts, count_csr with basis=None) against one annotation slice.
     max_row_total bounds the sum of a query's counts (default: the largest row total, one reduction); it decides
     whether the exact integer dots fit 32-bit accumulators."""
@@ -857,7 +863,7 @@ def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, c
         max_row_total = query_row_total_max(rowptr, vals)
     acc_bits = 32 if csc.max_m * max(int(max_row_total), 1) < 2 ** 32 else 64
     check(lib().skm_apply_sparse(_ptr(rowptr), _ptr(cols), _ptr(vals), nq, _ptr(csc.colptr), _ptr(csc.rows), _ptr(csc.mvals),
-                                 _ptr(csc.mnorm2), _ptr(csc.inv_m32), csc.n_ann, acc_bits, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2),
+                                 _ptr(csc.packed) if use_packed else None, _ptr(csc.mnorm2), _ptr(csc.inv_m32), csc.n_ann, acc_bits, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2),
                                  None, _stream()))
     return ApplyResult(top1, top2, s1, s2, None)
 

@@ -439,3 +439,29 @@ def test_learn_sparse_with_totals(a, k):
     _, _, t_all = E.learn_sparse_with_totals(batch, a, k, torch.zeros(len(seqs), dtype=torch.int32), n_ann)
     _, _, t_none = E.learn_sparse_with_totals(batch, a, k, torch.full((len(seqs),), -1, dtype=torch.int32), n_ann)
     assert torch.equal(t_all, totals) and torch.equal(t_none, totals)
+
+
+@pytest.mark.parametrize("a,k", [(2, 6), (5, 3), (1, 4)])
+def test_apply_sparse_packed_csc_identical(a, k):
+    """The 4-byte packed CSC (annotation << 16 | value, pipelined loads) gives bit-identical results to the 8-byte one,
+    and csc_build refuses to pack entries that do not fit 16 bits."""
+    rng = np.random.default_rng(k + 300)
+    train = _rand_seqs(rng, 1500, 20, 300)
+    n_ann = 41
+    ann = rng.integers(0, n_ann, size=len(train)).astype(np.int32)
+    tb = E.SequenceBatch.from_strings(train)
+    keys, vals = E.learn_sparse(tb, a, k, torch.from_numpy(ann), n_ann)
+    S = E.alphabet_tables(a).nsym ** k
+    queries = _rand_seqs(rng, 500, 0, 900) + ["", "ACD", "A" * 2000]
+    qb = E.SequenceBatch.from_strings(queries)
+    rowptr, cols, cvals = E.count_csr(qb, a, k, None)
+    csc = E.csc_build(keys, vals, S, n_ann, 0)
+    assert csc.packed is not None and csc.packed.numel() == csc.rows.numel()
+    r0 = E.apply_sparse(rowptr, cols, cvals, csc, use_packed=False)
+    r1 = E.apply_sparse(rowptr, cols, cvals, csc, use_packed=True)
+    assert torch.equal(r0.top1, r1.top1) and torch.equal(r0.top2, r1.top2) and torch.equal(r0.score1, r1.score1)
+    assert np.array_equal(r0.score2.cpu().numpy(), r1.score2.cpu().numpy(), equal_nan=True)
+    big = E.csc_build(keys, vals * 70000, S, n_ann, 0)           # entries beyond 16 bits: stays unpacked
+    assert big.packed is None
+    r2 = E.apply_sparse(rowptr, cols, cvals, big)
+    assert torch.equal(r2.top1, r0.top1)
