@@ -28,8 +28,9 @@
 
 namespace skm {
 
-constexpr int SP_SEG = ts_seg_cap(52);
-constexpr int SP_SYM_BYTES = ts_sym_bytes(SP_SEG);
+constexpr int SP_SEG = ts_seg_cap(28);                     // 7168 positions per staged segment
+constexpr int SP_SYM_BYTES = (ts_sym_bytes(SP_SEG) + 15) & ~15;
+template <typename KeyT> constexpr int sp_smem_bytes() { return SP_SYM_BYTES + SP_SEG * int(sizeof(KeyT)); }   // symbols + staged keys
 
 // keys[p] for every residue position p of [off[0], off[nseq]) (p = position of the window's LAST residue):
 //   MODE 0: column (col_of_code) or code, 32-bit, all-ones when invalid / filtered
@@ -47,12 +48,13 @@ __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *
     extern __shared__ __align__(128) uint8_t s_sym[];
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_ctl[4];
+    KeyT *s_keys = reinterpret_cast<KeyT *>(s_sym + SP_SYM_BYTES);       // one key per position of the staged segment
     ts_lut_init(s_lut, lut);
     __syncthreads();
     int64_t ann_row = -2;          // row whose annotation is cached
     uint64_t ann_base = ~0ull;
     ts_range_scan_rows<uint32_t>(res, nres, off, nseq, s_lut, s_sym, SP_SEG, k, nsym, pow_k1, /*origin=*/0, s_ctl,
-                                 [&](int64_t rel_end, int64_t row, uint32_t code, bool ok) {
+                                 [&](int64_t, int64_t row, uint32_t code, bool ok, int local) {
                                      KeyT key = invalid;
                                      if (ok) {
                                          if (MODE == 0) {
@@ -67,7 +69,10 @@ __global__ void __launch_bounds__(TS_THREADS) window_keys_kernel(const uint8_t *
                                              if (ann_base != ~0ull) key = KeyT(ann_base + code);
                                          }
                                      }
-                                     keys[rel_end] = key;
+                                     s_keys[local] = key;
+                                 },
+                                 [&](int64_t rel_a, int n) {         // coalesced copy of the segment's keys
+                                     for (int i = threadIdx.x; i < n; i += blockDim.x) keys[rel_a + i] = s_keys[i];
                                  });
 }
 
@@ -381,7 +386,7 @@ int skm_window_keys_u32(const uint8_t *d_residues, int64_t nres, const int64_t *
     int64_t grid = int64_t(sm_count()) * 8;
     const int64_t max_grid = (nres + SP_SEG - 1) / SP_SEG;
     if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
-    window_keys_kernel<0, uint32_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
+    window_keys_kernel<0, uint32_t><<<(unsigned)grid, TS_THREADS, sp_smem_bytes<uint32_t>(), st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
                                                                                       pow_k1, d_col_of_code, nullptr, 0, 0xFFFFFFFFu, d_keys);
     SKM_LAUNCH_CHECK("window_keys_kernel<0>");
     return SKM_OK;
@@ -431,7 +436,8 @@ int skm_learn_sparse(const uint8_t *d_residues, int64_t nres, const int64_t *d_o
     if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
     // positions outside [off[0], off[nseq]) are not written by the kernel
     SKM_CUDA_TRY(cudaMemsetAsync(keys_a, 0xFF, size_t(nres) * 8, st));
-    window_keys_kernel<1, uint64_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
+    SKM_CUDA_TRY(cudaFuncSetAttribute(window_keys_kernel<1, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem_bytes<uint64_t>()));
+    window_keys_kernel<1, uint64_t><<<(unsigned)grid, TS_THREADS, sp_smem_bytes<uint64_t>(), st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
                                                                                       pow_k1, nullptr, d_ann_id, S, invalid, keys_a);
     SKM_LAUNCH_CHECK("window_keys_kernel<1>");
     // keys are < 2^end_bit except the all-ones fill, whose low bits are all ones too: it still sorts last
@@ -517,7 +523,7 @@ int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, const int64_
     const int64_t max_grid = (nres + SP_SEG - 1) / SP_SEG;
     if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
     SKM_CUDA_TRY(cudaMemsetAsync(keys_a, 0xFF, size_t(nres) * 4, st));       // positions outside every sequence
-    window_keys_kernel<1, uint32_t><<<(unsigned)grid, TS_THREADS, SP_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
+    window_keys_kernel<1, uint32_t><<<(unsigned)grid, TS_THREADS, sp_smem_bytes<uint32_t>(), st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k,
                                                                                       pow_k1, nullptr, d_ann_id, S, invalid, keys_a,
                                                                                       (int32_t)ann_lo, (int32_t)(ann_lo + ann_n));
     SKM_LAUNCH_CHECK("window_keys_kernel<1, u32>");

@@ -204,13 +204,17 @@ __device__ __forceinline__ void cta_seq_range(const int64_t *__restrict__ off, i
 // start in the i-th 1/gridDim of the buffer.  emit(rel_end, row, code, ok) is called for EVERY residue
 // position of the range: rel_end = position of the window's last residue minus `origin`,
 // row = index of the sequence that holds it, ok = the window is valid.
+// emit also receives the index of the position inside the staged segment (0 .. n-1), and post(rel_a, n) is called by
+// ALL threads after every segment's scan (behind a barrier; another barrier follows): kernels that write one value per
+// position stage the values in shared memory in emit and copy them out coalesced in post — a thread's own positions
+// are 52 apart from its neighbour's, so direct global stores are fully uncoalesced.
 // s_sym: ts_sym_bytes(seg_cap) bytes; s_lut: 256 bytes (ts_lut_init done, barrier passed);
 // s_ctl: 4 x int64 of shared scratch.
-template <typename CodeT, typename Emit>
+template <typename CodeT, typename Emit, typename Post>
 __device__ __forceinline__ void ts_range_scan_rows(const uint8_t *__restrict__ res, int64_t nres,
                                                    const int64_t *__restrict__ off, int64_t nseq, const uint8_t *s_lut,
                                                    uint8_t *s_sym, int seg_cap, int k, CodeT nsym, CodeT pow_k1,
-                                                   int64_t origin, int64_t *s_ctl, Emit &&emit) {
+                                                   int64_t origin, int64_t *s_ctl, Emit &&emit, Post &&post) {
     const int tid = threadIdx.x;
     unsigned int *s_nstart = reinterpret_cast<unsigned int *>(s_ctl + 2);
     if (tid == 0) { cta_seq_range(off, nseq, &s_ctl[0], &s_ctl[1]); *s_nstart = 0; }
@@ -252,15 +256,18 @@ __device__ __forceinline__ void ts_range_scan_rows(const uint8_t *__restrict__ r
             int64_t row = l - 1;
             const int64_t to_abs = (g.base - TS_PAD) - int64_t(sym_addr);    // absolute position = shared address + to_abs
             const int64_t to_rel = to_abs - origin;
+            const uint32_t seg0 = sym_addr + uint32_t(g.lo);           // shared address of the segment's first symbol
             ts_scan_chunk<CodeT>(
                 sym_addr, i0, i1, k, nsym, pow_k1,
-                [&](uint32_t p, CodeT code, bool ok) { emit(int64_t(p) + to_rel, row, code, ok); },
+                [&](uint32_t p, CodeT code, bool ok) { emit(int64_t(p) + to_rel, row, code, ok, int(p - seg0)); },
                 [&](uint32_t p) {
                     const int64_t pos = int64_t(p) + to_abs;
                     do { ++row; } while (row + 1 < nseq && __ldg(off + row + 1) <= pos);   // skips empty sequences
                 });
         }
         tail = ts_tail_read(s_sym, g, k);
+        __syncthreads();
+        post(a - origin, g.hi - g.lo);
         first = false;
         cur += nstart;
         a = b;

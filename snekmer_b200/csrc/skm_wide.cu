@@ -25,8 +25,9 @@
 
 namespace skm {
 
-constexpr int WD_SEG = ts_seg_cap(52);
-constexpr int WD_SYM_BYTES = ts_sym_bytes(WD_SEG);
+constexpr int WD_SEG = ts_seg_cap(28);
+constexpr int WD_SYM_BYTES = (ts_sym_bytes(WD_SEG) + 15) & ~15;
+constexpr int WD_SMEM_BYTES = WD_SYM_BYTES + WD_SEG * 8;          // symbols + one staged 64-bit key per position
 constexpr uint64_t WD_NONE = ~0ull;
 
 // keys[p] = 64-bit code of the window whose LAST residue sits at position p, all-ones when invalid
@@ -37,10 +38,15 @@ __global__ void __launch_bounds__(TS_THREADS) window_codes64_kernel(const uint8_
     extern __shared__ __align__(128) uint8_t s_sym[];
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_ctl[4];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_sym + WD_SYM_BYTES);
     ts_lut_init(s_lut, lut);
     __syncthreads();
+    // keys are staged per segment and copied out coalesced (a thread's positions are 28 apart from its neighbour's)
     ts_range_scan_rows<uint64_t>(res, nres, off, nseq, s_lut, s_sym, WD_SEG, k, nsym, pow_k1, /*origin=*/0, s_ctl,
-                                 [&](int64_t rel_end, int64_t, uint64_t code, bool ok) { keys[rel_end] = ok ? code : WD_NONE; });
+                                 [&](int64_t, int64_t, uint64_t code, bool ok, int local) { s_keys[local] = ok ? code : WD_NONE; },
+                                 [&](int64_t rel_a, int n) {
+                                     for (int i = threadIdx.x; i < n; i += blockDim.x) keys[rel_a + i] = s_keys[i];
+                                 });
 }
 
 __global__ void __launch_bounds__(256) iota_u32_kernel(uint32_t *__restrict__ out, int64_t n) {
@@ -173,7 +179,8 @@ static int launch_window_codes64(const uint8_t *d_residues, int64_t nres, const 
     int64_t grid = int64_t(sm_count()) * 8;
     const int64_t max_grid = (nres + WD_SEG - 1) / WD_SEG;
     if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
-    window_codes64_kernel<<<(unsigned)grid, TS_THREADS, WD_SYM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint64_t)nsym, k, pow_k1, d_keys);
+    SKM_CUDA_TRY(cudaFuncSetAttribute(window_codes64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM_BYTES));
+    window_codes64_kernel<<<(unsigned)grid, TS_THREADS, WD_SMEM_BYTES, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint64_t)nsym, k, pow_k1, d_keys);
     SKM_LAUNCH_CHECK("window_codes64_kernel");
     return SKM_OK;
 }
