@@ -150,17 +150,34 @@ def export_npz(skmv_path: str, npz_path: str) -> None:
 # ---------------------------------------------------------------------------
 # count matrices (.skmc)  <->  kmer-counts-*.csv
 # ---------------------------------------------------------------------------
-def write_counts(path: str, rows: Sequence[str], kmers: Sequence[str], seq_count: np.ndarray, kmer_count: np.ndarray, M: np.ndarray) -> None:
-    """rows include ``Totals`` (first) exactly like the CSV; M int64 [R, K] dense in, CSR on disk."""
-    M = np.asarray(M, dtype=np.int64)
-    r, c = np.nonzero(M)
-    rowptr = np.zeros(M.shape[0] + 1, dtype=np.int64)
-    np.cumsum(np.bincount(r, minlength=M.shape[0]), out=rowptr[1:])
+def write_counts_csr(path: str, rows: Sequence[str], kmers: Sequence[str], seq_count: np.ndarray, kmer_count: np.ndarray,
+                     rowptr: np.ndarray, cols: np.ndarray, vals: np.ndarray) -> None:
+    """rows include ``Totals`` (first) exactly like the CSV; the matrix is given as CSR over the k-mer list."""
     rb, ro = _strings_to_arrays(rows)
     kb, ko = _strings_to_arrays(kmers)
     write_container(path, "counts", {"nrows": len(rows), "K": len(kmers)},
                     {"rows": rb, "row_offsets": ro, "kmers": kb, "kmer_offsets": ko, "seq_count": np.asarray(seq_count, dtype=np.int64),
-                     "kmer_count": np.asarray(kmer_count, dtype=np.int64), "rowptr": rowptr, "cols": c.astype(np.int32), "vals": M[r, c]})
+                     "kmer_count": np.asarray(kmer_count, dtype=np.int64), "rowptr": np.asarray(rowptr, dtype=np.int64),
+                     "cols": np.asarray(cols, dtype=np.int32), "vals": np.asarray(vals, dtype=np.int64)})
+
+
+def write_counts(path: str, rows: Sequence[str], kmers: Sequence[str], seq_count: np.ndarray, kmer_count: np.ndarray, M: np.ndarray) -> None:
+    """Dense int64 [R, K] in, CSR on disk."""
+    M = np.asarray(M, dtype=np.int64)
+    r, c = np.nonzero(M)
+    rowptr = np.zeros(M.shape[0] + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r, minlength=M.shape[0]), out=rowptr[1:])
+    write_counts_csr(path, rows, kmers, seq_count, kmer_count, rowptr, c.astype(np.int32), M[r, c])
+
+
+def read_counts_csr(path: str, mmap: bool = True) -> Dict:
+    """The side-car as stored (no dense matrix): rows, kmers, seq_count, kmer_count, rowptr, cols, vals."""
+    kind, attrs, a = read_container(path, mmap)
+    if kind != "counts":
+        raise ValueError(f"{path}: holds '{kind}', not counts")
+    return dict(rows=_arrays_to_strings(a["rows"], a["row_offsets"]), kmers=_arrays_to_strings(a["kmers"], a["kmer_offsets"]),
+                seq_count=np.array(a["seq_count"]), kmer_count=np.array(a["kmer_count"]), rowptr=np.array(a["rowptr"]),
+                cols=np.array(a["cols"]), vals=np.array(a["vals"]))
 
 
 def read_counts(path: str, mmap: bool = True):
