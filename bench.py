@@ -340,7 +340,7 @@ def run_learn(ctx, args):
             "config": {"workload": f"C3 shape: {args.nseq} proteins/GPU, 6-letter alphabet k=8 (S=1,679,616), 20k annotations Zipf(1.1), 30% unannotated; sparse COO matrix",
                        "nnz_rank0": nnz, "l2": "inputs 0.44 GB, keys 3.5 GB larger than L2",
                        "parallelism": f"sequence-sharded x{ctx.world}" + (", all_to_all of COO runs by annotation range + local merge" if ctx.world > 1 else "")},
-            "clocks": clocks, "gpu_launches": 14 * args.steps,
+            "clocks": clocks, "gpu_launches": 110 * args.steps,      # ~8 annotation slices x (fill, keys, histogram, 4 sort passes, RLE x2, append x2) + gather, Totals, column sums (profiles/r2f_launches_learn.csv)
             "roofline": {"bound": "hbm", "kernel": "learn step (Totals table + gather by annotation + 32-bit keys + radix sort + run-length encode per annotation slice)", "achieved": alg_bytes / (ms * 1e-3) / 1e9,
                          "peak": peak, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg_bytes, "kernel_ms": ms,
