@@ -164,9 +164,9 @@ __device__ __forceinline__ void top2x_push(Top2x &t, float f, unsigned long long
     }
 }
 
-constexpr int SPA_THREADS = 1024;
+constexpr int SPA_THREADS = 512;
 constexpr int SPA_EB = 512;        // query entries staged per block
-constexpr int SPA_SEG = 256;       // CSC entries per segment (8 per lane)
+constexpr int SPA_SEG = 512;       // CSC entries per segment (16 per lane)
 
 // One CTA per query (grid-stride).  acc: one integer per annotation in shared memory (AccT = uint32 when every dot
 // fits 32 bits — the host checks max(M) * max row total < 2^32 — else uint64).
@@ -250,29 +250,27 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
                     // one 32-bit word per CSC entry (annotation << 16 | value): half the loads and registers, which pays
                     // for a software pipeline — the next item's 8 loads are issued before the current item's atomics
                     // (22 % of the samples of the unpacked kernel wait on the loads of the item they are about to use)
-                    uint32_t cur[SPA_SEG / 32], nxt[SPA_SEG / 32];
-                    int j = __shfl_sync(FULL, ej, 0), seg = __shfl_sync(FULL, es, 0);
-                    {
+                    uint32_t cur[SPA_SEG / 32], n1[SPA_SEG / 32], n2[SPA_SEG / 32];
+                    auto fetch = [&](int i, uint32_t (&dst)[SPA_SEG / 32]) -> uint32_t {
+                        const int j = __shfl_sync(FULL, ej, i), seg = __shfl_sync(FULL, es, i);
                         const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
                         const int n = min(SPA_SEG, s_len[j] - seg * SPA_SEG);
 #pragma unroll
-                        for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; cur[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
-                    }
+                        for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; dst[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
+                        return s_cnt[j];
+                    };
+                    // two items of look-ahead: 16 loads per lane in flight while the current item's atomics run
+                    uint32_t c0 = fetch(0, cur), c1 = 0, c2 = 0;
+                    if (in_round > 1) c1 = fetch(1, n1);
                     for (int i = 0; i < in_round; ++i) {
-                        const AccT cnt = AccT(s_cnt[j]);
-                        if (i + 1 < in_round) {
-                            j = __shfl_sync(FULL, ej, i + 1);
-                            seg = __shfl_sync(FULL, es, i + 1);
-                            const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
-                            const int n = min(SPA_SEG, s_len[j] - seg * SPA_SEG);
-#pragma unroll
-                            for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; nxt[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
-                        }
+                        if (i + 2 < in_round) c2 = fetch(i + 2, n2);
+                        const AccT cnt = AccT(c0);
 #pragma unroll
                         for (int u = 0; u < SPA_SEG / 32; ++u)
                             if (cur[u] & 0xFFFFu) atomicAdd(&acc[cur[u] >> 16], cnt * AccT(cur[u] & 0xFFFFu));      // values are >= 1
 #pragma unroll
-                        for (int u = 0; u < SPA_SEG / 32; ++u) cur[u] = nxt[u];
+                        for (int u = 0; u < SPA_SEG / 32; ++u) { cur[u] = n1[u]; n1[u] = n2[u]; }
+                        c0 = c1; c1 = c2;
                     }
                     continue;
                 }
