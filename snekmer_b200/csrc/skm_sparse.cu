@@ -165,7 +165,8 @@ __device__ __forceinline__ void top2x_push(Top2x &t, float f, unsigned long long
 }
 
 constexpr int SPA_THREADS = 512;
-constexpr int SPA_EB = 512;        // query entries staged per block
+constexpr int SPA_EB = 512;        // query entries staged per block (one per thread: SPA_EB <= SPA_THREADS)
+static_assert(SPA_EB <= SPA_THREADS, "the staging step gives every staged query entry its own thread");
 constexpr int SPA_SEG = 512;       // CSC entries per segment (16 per lane)
 
 // One CTA per query (grid-stride).  acc: one integer per annotation in shared memory (AccT = uint32 when every dot
