@@ -59,3 +59,20 @@ def test_vectors_npz_export_matches_reference(tmp_path):
     z = np.load(out)
     assert list(z["kmerlist"]) == kmerlist and list(z["ids"]) == list(d["synA_ids"]) and list(z["seqs"]) == list(d["synA_seqs"])
     assert np.array_equal(z["lengths"], d["synA_lengths"]) and z["vecs"].dtype == np.float64 and np.array_equal(z["vecs"], vecs.astype(np.float64))
+
+
+def test_counts_csr_roundtrip_without_dense(tmp_path):
+    rows = ["Totals", "famA", "famB"]
+    kmers = ["AAA", "AAC", "ACA", "CAA"]
+    rowptr = np.array([0, 3, 5, 6])
+    cols = np.array([0, 1, 3, 0, 3, 1], dtype=np.int32)
+    vals = np.array([7, 2, 5, 4, 5, 2], dtype=np.int64)
+    p = str(tmp_path / "m.skmc")
+    SC.write_counts_csr(p, rows, kmers, np.array([9, 4, 5]), np.array([14, 9, 2]), rowptr, cols, vals)
+    d = SC.read_counts_csr(p)
+    assert d["rows"] == rows and d["kmers"] == kmers
+    assert np.array_equal(d["rowptr"], rowptr) and np.array_equal(d["cols"], cols) and np.array_equal(d["vals"], vals)
+    t = SC.read_counts(p)                       # the dense view of the same file
+    want = np.zeros((3, 4), dtype=np.int64)
+    want[np.repeat(np.arange(3), np.diff(rowptr)), cols] = vals
+    assert np.array_equal(t.M, want) and t.seq_count.tolist() == [9, 4, 5] and t.kmer_count.tolist() == [14, 9, 2]
