@@ -95,8 +95,26 @@ SKM_API int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres,
                          uint64_t res_base, uint64_t *d_count,
                          uint64_t *d_first, skm_stream_t stream);
 
+/* (a7) order-only variant of pass 1 for min_filter = 0 (kmerize.smk:89-104 keeps every k-mer that
+ * occurs, so the basis is fully determined by the first positions): the shard is walked front to
+ * back in chunks of sequences (about first_chunk_res residues, then `growth` times more per chunk;
+ * 0 = defaults) and the walk ends ON THE DEVICE as soon as every code of the space has a first
+ * position — later chunks' CTAs return at once, no host synchronisation.  A space that never
+ * saturates costs one full pass, like skm_basis_accumulate.  Code spaces up to
+ * skm_basis_order_max_space() (shared-memory tables).  d_first as in skm_basis_accumulate (init
+ * all-ones); d_state is int32[4], zero-initialised by the caller ([0] = saturated, [2] = codes
+ * seen when last evaluated).  h_offsets is the HOST copy of d_offsets (chunk boundaries). */
+SKM_API int skm_basis_order_max_space(void);
+SKM_API int skm_basis_first_progressive(const uint8_t *d_residues, int64_t nres,
+                                const int64_t *d_offsets, const int64_t *h_offsets,
+                                int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                                uint64_t res_base, uint64_t *d_first, int32_t *d_state,
+                                int64_t first_chunk_res, int growth, skm_stream_t stream);
+
 /* kmerize.smk:102-104 + dict insertion order: keep codes with
- * count > min_filter, order by first occurrence.  Writes d_basis_codes[0..K),
+ * count > min_filter, order by first occurrence.  d_count and d_basis_counts may both be NULL
+ * (order-only tables of skm_basis_first_progressive; min_filter must be 0): every code with a
+ * first position is kept.  Writes d_basis_codes[0..K),
  * d_basis_counts[0..K), d_col_of_code[c] = column or -1 for every c < S, and K
  * to *d_K (device int64).  Capacity of the two basis arrays: S. */
 SKM_API size_t skm_basis_finalize_workspace(int64_t S);
@@ -299,7 +317,8 @@ SKM_API int skm_apply_dense(const int32_t *d_Q, int64_t nq, int64_t K,
  * skm_apply_tc_prepare (once per learned matrix; this call synchronises the stream to read
  * back the largest entry).  d_planes needs skm_apply_tc_planes_bytes() bytes, 128-byte
  * aligned.  skm_apply_tc writes *d_status = 1 (device int) when a query count exceeded 255:
- * the outputs are then invalid and the caller must use skm_apply_dense.  Scores are
+ * the outputs of THOSE rows are invalid and the caller re-scores them with skm_apply_dense
+ * (skm_rows_out_of_range_i32 lists them); all other rows are exact.  Scores are
  * dot * (1/||q||) * (1/||m||) in float64; outputs as skm_apply_dense. */
 SKM_API size_t skm_apply_tc_planes_bytes(int64_t n_ann, int64_t K);
 SKM_API int skm_apply_tc_prepare(const int64_t *d_M, int64_t n_ann, int64_t K, uint8_t *d_planes,
@@ -339,6 +358,24 @@ SKM_API int skm_scatter_add_i64(const int64_t *d_src, int64_t rows, int64_t cols
                         const int64_t *d_row_map, const int64_t *d_col_map,
                         int64_t *d_dst, int64_t dst_rows, int64_t dst_cols,
                         skm_stream_t stream);
+
+/* Compact transports of a dense count matrix [rows, cols] (in_bits 32 = int32, 16 = uint16) for the trip back to the
+ * host — the reference's own vectorize payload is the 0/1 presence matrix (kmerize.smk:112-120,132-139).
+ * skm_pack_counts_u8: uint8 counts; entries >= 255 are written as 255 and appended (unordered) to the escape list
+ * (row, col, count), *d_n_esc (device int64) = how many there are (may exceed esc_capacity: the list is then
+ * truncated and the caller must retry with a larger one).  Lossless: out[r, c] < 255 is the count itself.
+ * skm_pack_presence_bits: bit (c & 7) of byte c >> 3 of a row of ceil(cols / 8) bytes is counts[r, c] > 0. */
+SKM_API int skm_pack_counts_u8(const void *d_counts, int64_t rows, int64_t cols, int in_bits, uint8_t *d_out,
+                       int32_t *d_esc_row, int32_t *d_esc_col, int32_t *d_esc_val, int64_t esc_capacity,
+                       int64_t *d_n_esc, skm_stream_t stream);
+SKM_API int skm_pack_presence_bits(const void *d_counts, int64_t rows, int64_t cols, int in_bits, uint8_t *d_out,
+                           skm_stream_t stream);
+
+/* Rows of an int32 matrix holding an element outside [lo, hi], appended (unordered) to d_rows_out; *d_n_out
+ * (device int64) = how many.  skm_apply_tc scores rows with counts in 0..255; the caller re-scores the listed
+ * rows with skm_apply_dense (apply.smk:278-289 has no such limit). */
+SKM_API int skm_rows_out_of_range_i32(const int32_t *d_X, int64_t rows, int64_t cols, int32_t lo, int32_t hi,
+                              int32_t *d_rows_out, int64_t capacity, int64_t *d_n_out, skm_stream_t stream);
 
 /* (a11) per-sequence counts as CSR WITHOUT a device-wide sort: a warp scans one sequence, sorts its window keys in
  * shared memory (bitonic network) and run-length encodes them; longer sequences get a CTA.  Same results as

@@ -42,6 +42,8 @@ SIGNATURES = {
     "skm_reduce_bytes": (_int, [_p, _i64, _p, _p, _p]),
     "skm_encode_windows": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _int, _p, _p]),
     "skm_basis_accumulate": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _u64, _p, _p, _p]),
+    "skm_basis_order_max_space": (_int, []),
+    "skm_basis_first_progressive": (_int, [_p, _i64, _p, _p, _i64, _p, _int, _int, _u64, _p, _p, _i64, _int, _p]),
     "skm_basis_finalize_workspace": (_sz, [_i64]),
     "skm_basis_finalize": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_basis_colmap": (_int, [_p, _i64, _i64, _p, _p]),
@@ -86,6 +88,9 @@ SIGNATURES = {
     "skm_row_norm2_i32": (_int, [_p, _i64, _i64, _p, _p]),
     "skm_row_norm2_i64": (_int, [_p, _i64, _i64, _p, _p]),
     "skm_gather_columns": (_int, [_p, _i64, _i64, _int, _p, _i64, _p, _p]),
+    "skm_pack_counts_u8": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _i64, _p, _p]),
+    "skm_pack_presence_bits": (_int, [_p, _i64, _i64, _int, _p, _p]),
+    "skm_rows_out_of_range_i32": (_int, [_p, _i64, _i64, C.c_int32, C.c_int32, _p, _i64, _p, _p]),
     "skm_scatter_add_i64": (_int, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _p]),
 }
 

@@ -13,6 +13,8 @@
 // and flushed with S atomics per CTA; large ones go straight to L2 atomics
 // (low contention because the table is large) with a read-before-min filter.
 // Algorithmic bytes: R residues + 8 (N+1) offsets + 24 S table.
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "skm_common.cuh"
@@ -28,29 +30,40 @@ constexpr int BS_SYM_BYTES = ts_sym_bytes(BS_SEG);
 // One kernel for both table kinds.  SMALL: per-CTA tables in shared memory ([S] counts, [S] first positions
 // relative to the CTA's residue range), merged into the global tables with S atomics per CTA.  !SMALL: the
 // tables are large and L2-resident; windows update them directly (low contention because S is large).
-template <bool SMALL>
+// ORDER = order-only mode (min_filter == 0 callers that do not need occurrence counts): no count table, and the launch
+// is one CHUNK of a front-to-back walk over the shard — `state[0]` is the device-side "every code of the space has a
+// first position" flag: CTAs of later chunks see it and return at once, and the last CTA of a chunk (ticket in
+// state[1]) re-evaluates it.  first[c] of a code is final as soon as it is set by a chunk (chunks are walked in
+// position order), so once all S codes are seen the rest of the shard cannot change the basis order.
+template <bool SMALL, bool ORDER>
 __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__restrict__ res, int64_t nres,
                                                            const int64_t *__restrict__ off, int64_t nseq,
                                                            const uint8_t *__restrict__ lut, uint32_t nsym, int k,
                                                            uint32_t pow_k1, int S, uint64_t res_base,
                                                            unsigned long long *__restrict__ g_count,
-                                                           unsigned long long *__restrict__ g_first) {
+                                                           unsigned long long *__restrict__ g_first,
+                                                           int *__restrict__ state) {
     extern __shared__ __align__(128) uint8_t s_raw[];   // symbol buffer, then (SMALL) the two tables
     __shared__ uint8_t s_lut[256];
     __shared__ int64_t s_range[2];
     __shared__ unsigned int s_nstart;
+    __shared__ int s_flag;
+    if (ORDER) {
+        if (threadIdx.x == 0) s_flag = *reinterpret_cast<volatile int *>(state);
+        __syncthreads();
+        if (s_flag) return;                             // saturated by an earlier chunk: nothing left to learn
+    }
     uint8_t *s_sym = s_raw;
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw + BS_SYM_BYTES), *s_min = s_cnt + S;
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_raw + BS_SYM_BYTES), *s_min = ORDER ? s_cnt : s_cnt + S;
     uint32_t sym_addr = smem_addr(s_sym), cnt_addr = smem_addr(s_cnt), min_addr = smem_addr(s_min);
     asm volatile("" : "+r"(sym_addr), "+r"(cnt_addr), "+r"(min_addr));   // keep the window addresses in registers
     const int tid = threadIdx.x;
     ts_lut_init(s_lut, lut);
-    if (SMALL) for (int i = tid; i < S; i += blockDim.x) { s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }
+    if (SMALL) for (int i = tid; i < S; i += blockDim.x) { if (!ORDER) s_cnt[i] = 0; s_min[i] = 0xFFFFFFFFu; }
     if (tid == 0) { cta_seq_range(off, nseq, &s_range[0], &s_range[1]); s_nstart = 0; }
     __syncthreads();
     const int64_t lo = s_range[0], hi = s_range[1];
-    if (lo >= hi) return;
-    const int64_t r_lo = __ldg(off + lo), r_hi = __ldg(off + hi);
+    const int64_t r_lo = (lo < hi) ? __ldg(off + lo) : 0, r_hi = (lo < hi) ? __ldg(off + hi) : 0;
     int64_t cur = lo;                 // first sequence that starts at or after `a`
     bool first = true;
     uint32_t tail = 0;
@@ -81,7 +94,7 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
                 if (ok) {
                     const uint32_t rel = p + to_rel;
                     if (SMALL) {
-                        reds_add_u32(cnt_addr + (code << 2), 1u);
+                        if (!ORDER) reds_add_u32(cnt_addr + (code << 2), 1u);
                         if (rel < s_min[code]) reds_min_u32(min_addr + (code << 2), rel);
                     } else {
                         atomicAdd(g_count + code, 1ull);
@@ -98,13 +111,40 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
         __syncthreads();
         if (tid == 0) s_nstart = 0;    // ordered before the next atomicAdd by the barrier after staging
     }
-    if (SMALL) {
+    if (SMALL && lo < hi) {
         for (int i = tid; i < S; i += blockDim.x) {
-            const uint32_t c = s_cnt[i];
-            if (c) {
-                atomicAdd(g_count + i, (unsigned long long)c);
-                if (g_first) atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + s_min[i]));
+            if (ORDER) {
+                const uint32_t m = s_min[i];
+                if (m != 0xFFFFFFFFu) atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + m));
+            } else {
+                const uint32_t c = s_cnt[i];
+                if (c) {
+                    atomicAdd(g_count + i, (unsigned long long)c);
+                    if (g_first) atomicMin(g_first + i, (unsigned long long)(res_base + uint64_t(r_lo) + s_min[i]));
+                }
             }
+        }
+    }
+    if (ORDER) {
+        // the last CTA of this chunk to get here counts the codes that have a first position
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_flag = (atomicAdd(state + 1, 1) == int(gridDim.x) - 1);
+        __syncthreads();
+        if (!s_flag) return;
+        __threadfence();
+        int seen = 0;
+        for (int i = tid; i < S; i += blockDim.x) seen += (__ldcg(g_first + i) != ~0ull);
+        __shared__ int s_seen;
+        if (tid == 0) s_seen = 0;
+        __syncthreads();
+        if (seen) atomicAdd(&s_seen, seen);
+        __syncthreads();
+        if (tid == 0) {
+            state[1] = 0;                               // ticket ready for the next chunk's launch
+            state[2] = s_seen;
+            if (s_seen == S) state[0] = 1;
+            __threadfence();
         }
     }
 }
@@ -112,7 +152,7 @@ __global__ void __launch_bounds__(TS_THREADS) basis_kernel(const uint8_t *__rest
 __global__ void basis_keys_kernel(const uint64_t *__restrict__ count, const uint64_t *__restrict__ first, int64_t S,
                                   uint64_t min_filter, uint64_t *__restrict__ keys, uint64_t *__restrict__ vals) {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < S; i += int64_t(gridDim.x) * blockDim.x) {
-        keys[i] = (count[i] > min_filter) ? first[i] : ~0ull;
+        keys[i] = (count ? count[i] > min_filter : true) ? first[i] : ~0ull;     // no counts: every code that was seen
         vals[i] = uint64_t(i);
     }
 }
@@ -127,7 +167,7 @@ __global__ void basis_emit_kernel(const uint64_t *__restrict__ keys_sorted, cons
         const bool kept = key != ~0ull;
         if (kept) {
             basis_codes[j] = code;
-            basis_counts[j] = count[code];
+            if (basis_counts) basis_counts[j] = count[code];
             if (col_of_code) col_of_code[code] = (int32_t)j;
             const bool last = (j + 1 == S) || (keys_sorted[j + 1] == ~0ull);
             if (last) *K_out = j + 1;
@@ -149,6 +189,19 @@ __global__ void colmap_scatter_kernel(const uint64_t *__restrict__ codes, int64_
 }
 
 static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+// CTAs of a basis_kernel launch over nres residues with `smem` bytes of dynamic shared memory each
+static int64_t basis_grid(int64_t nres, size_t smem) {
+    int per_sm = int((227 * 1024) / (smem + 1536));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = int64_t(sm_count()) * per_sm;
+    const int64_t min_grid = (nres >> 30) + 1;           // keep each CTA's residue range well below 2^32
+    if (grid < min_grid) grid = min_grid;
+    const int64_t max_grid = (nres + BS_SEG - 1) / BS_SEG;   // no point in CTAs with less than a segment
+    if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
+    return grid;
+}
 
 }  // namespace skm
 
@@ -177,23 +230,66 @@ int skm_basis_accumulate(const uint8_t *d_residues, int64_t nres, const int64_t 
     for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
     const bool small = S <= SMALL_S;
     const size_t smem = size_t(BS_SYM_BYTES) + (small ? size_t(S) * 8 : 0);
-    int per_sm = int((227 * 1024) / (smem + 1536));
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = int64_t(sm_count()) * per_sm;
-    const int64_t min_grid = (nres >> 30) + 1;           // keep each CTA's residue range well below 2^32
-    if (grid < min_grid) grid = min_grid;
-    const int64_t max_grid = (nres + BS_SEG - 1) / BS_SEG;   // no point in CTAs with less than a segment
-    if (grid > max_grid) grid = max_grid < 1 ? 1 : max_grid;
+    const int64_t grid = basis_grid(nres, smem);
     if (small) {
-        auto kern = basis_kernel<true>;
+        auto kern = basis_kernel<true, false>;
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst);
+        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst, nullptr);
     } else {
-        auto kern = basis_kernel<false>;
-        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst);
+        auto kern = basis_kernel<false, false>;
+        kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, (int)S, res_base, cnt, fst, nullptr);
     }
     SKM_LAUNCH_CHECK("basis_accumulate");
+    return SKM_OK;
+}
+
+int skm_basis_order_max_space(void) { return (int)skm::SMALL_S; }
+
+int skm_basis_first_progressive(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets,
+                                const int64_t *h_offsets, int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                                uint64_t res_base, uint64_t *d_first, int32_t *d_state, int64_t first_chunk_res,
+                                int growth, skm_stream_t stream) {
+    using namespace skm;
+    int rc = check_common(d_residues, nres, d_offsets, nseq, d_lut, nsym, k);
+    if (rc) return rc;
+    unsigned __int128 S128;
+    code_space(nsym, k, &S128);
+    if (S128 > (unsigned __int128)SMALL_S) {
+        set_error("skm_basis_first_progressive: code space %d^%d exceeds %lld (use skm_basis_accumulate)", nsym, k, (long long)SMALL_S);
+        return SKM_ERR_UNSUPPORTED;
+    }
+    if (!d_first || !d_state || (nseq > 0 && !h_offsets)) { set_error("skm_basis_first_progressive: NULL argument"); return SKM_ERR_INVALID; }
+    if (nseq == 0 || nres == 0) return SKM_OK;
+    if (!ts_supported(nsym, k)) { set_error("skm_basis_first_progressive: nsym=%d k=%d outside the kernel envelope", nsym, k); return SKM_ERR_UNSUPPORTED; }
+    if (first_chunk_res <= 0) first_chunk_res = 4ll << 20;
+    if (growth < 2) growth = 4;
+    const int64_t S = (int64_t)S128;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto *fst = reinterpret_cast<unsigned long long *>(d_first);
+    uint32_t pow_k1 = 1;
+    for (int i = 0; i + 1 < k; ++i) pow_k1 *= (uint32_t)nsym;
+    const size_t smem = size_t(BS_SYM_BYTES) + size_t(S) * 4;
+    auto kern = basis_kernel<true, true>;
+    SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // chunks of sequences, front to back: ~first_chunk_res residues, then `growth` times more each time
+    int64_t s_lo = 0, want = first_chunk_res;
+    while (s_lo < nseq) {
+        const int64_t r_lo = h_offsets[s_lo];
+        int64_t s_hi = nseq;
+        if (h_offsets[nseq] - r_lo > want + want / 2) {          // otherwise the rest goes in one launch
+            const int64_t *it = std::lower_bound(h_offsets + s_lo + 1, h_offsets + nseq, r_lo + want);
+            s_hi = it - h_offsets;
+        }
+        const int64_t chunk_res = h_offsets[s_hi] - r_lo;
+        if (chunk_res > 0) {
+            const int64_t grid = basis_grid(chunk_res, smem);
+            kern<<<(unsigned)grid, TS_THREADS, smem, st>>>(d_residues, nres, d_offsets + s_lo, s_hi - s_lo, d_lut, (uint32_t)nsym, k,
+                                                           pow_k1, (int)S, res_base, nullptr, fst, d_state);
+            SKM_LAUNCH_CHECK("basis_first_progressive");
+        }
+        s_lo = s_hi;
+        want *= growth;
+    }
     return SKM_OK;
 }
 
@@ -211,7 +307,9 @@ int skm_basis_finalize(const uint64_t *d_count, const uint64_t *d_first, int64_t
                        void *workspace, size_t workspace_bytes, skm_stream_t stream) {
     using namespace skm;
     if (S <= 0 || S > SKM_DENSE_MAX_SPACE) { set_error("skm_basis_finalize: S=%lld out of range", (long long)S); return SKM_ERR_INVALID; }
-    if (!d_count || !d_first || !d_basis_codes || !d_basis_counts || !d_K) { set_error("skm_basis_finalize: NULL argument"); return SKM_ERR_INVALID; }
+    if (!d_first || !d_basis_codes || !d_K) { set_error("skm_basis_finalize: NULL argument"); return SKM_ERR_INVALID; }
+    if (!d_count && (min_filter > 0 || d_basis_counts)) { set_error("skm_basis_finalize: without d_count only min_filter = 0 and no d_basis_counts"); return SKM_ERR_INVALID; }
+    if (d_count && !d_basis_counts) { set_error("skm_basis_finalize: NULL d_basis_counts"); return SKM_ERR_INVALID; }
     if (min_filter < 0) min_filter = 0;   // count > negative is always true for present k-mers; absent ones (count 0) must stay out
     const size_t need = skm_basis_finalize_workspace(S);
     if (!workspace || workspace_bytes < need) { set_error("skm_basis_finalize: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }

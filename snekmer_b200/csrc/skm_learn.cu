@@ -88,17 +88,29 @@ __global__ void learn_totals_kernel(const int64_t *__restrict__ M, const int64_t
 template <typename T>
 __global__ void __launch_bounds__(256) row_norm2_kernel(const T *__restrict__ X, int64_t rows, int64_t cols,
                                                         double *__restrict__ out) {
-    // one warp per row; exact integer accumulation in 64 bits per lane, then double
+    // one warp per row; EXACT integer accumulation (128 bits per lane, so that sums of squares of 64-bit counts cannot
+    // wrap), one conversion to double at the end: below 2^53 — every real matrix — the result is the exact integer,
+    // the same value skm_csc_build's integer sums and sklearn's float64 accumulation give.
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     for (int64_t r = warp; r < rows; r += nwarps) {
         const T *x = X + r * cols;
-        double acc = 0.0;
-        for (int64_t c = lane; c < cols; c += 32) { const double v = (double)x[c]; acc += v * v; }
+        unsigned __int128 acc = 0;
+        for (int64_t c = lane; c < cols; c += 32) {
+            const int64_t v = (int64_t)x[c];
+            const unsigned long long a = (unsigned long long)(v < 0 ? -v : v);
+            acc += (unsigned __int128)a * a;
+        }
+        unsigned long long lo = (unsigned long long)acc, hi = (unsigned long long)(acc >> 64);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (lane == 0) out[r] = acc;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long lo2 = __shfl_xor_sync(FULL, lo, o), hi2 = __shfl_xor_sync(FULL, hi, o);
+            const unsigned long long s = lo + lo2;
+            hi += hi2 + (s < lo ? 1ull : 0ull);
+            lo = s;
+        }
+        if (lane == 0) out[r] = hi ? (double)hi * 18446744073709551616.0 + (double)lo : (double)lo;
     }
 }
 

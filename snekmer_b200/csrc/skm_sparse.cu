@@ -85,7 +85,10 @@ __global__ void coo_finish_kernel(const uint64_t *__restrict__ uniq, const int64
 }
 
 // ---- CSC build -------------------------------------------------------------------------------
-// ||m_a||^2 as exact integers (order-independent, hence reproducible); requires sum v^2 < 2^64
+// ||m_a||^2 as exact integers (order-independent, hence reproducible).  Entries are < 2^31 (skm_csc_build's callers
+// check max_m) and an annotation's entries sum to at most the residues it was learned from, so sum v^2 <= (sum v)^2
+// stays below 2^64 while an annotation holds fewer than 2^32 k-mer occurrences; the dense kernel (row_norm2_kernel)
+// accumulates in 128 bits and gives the same integer.
 __global__ void __launch_bounds__(256) coo_row_norm2_kernel(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
                                                             int64_t nnz, uint64_t S, unsigned long long *__restrict__ norm2) {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x) {

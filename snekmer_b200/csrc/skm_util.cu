@@ -61,6 +61,83 @@ __global__ void __launch_bounds__(256) gather_sequences_kernel(const uint8_t *__
     }
 }
 
+
+// ---- compact transports of a dense count matrix (pipeline.vectorize_host) ------------------------------------
+// uint8 counts saturated at 255 + an escape list (row, col, count) of the entries that do not fit: lossless, a
+// quarter of the int32 bytes.  One thread per 4 consecutive elements of the flattened matrix (one output word).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_u8_kernel(const T *__restrict__ in, int64_t total, int64_t cols,
+                                                      uint8_t *__restrict__ out, int32_t *__restrict__ esc_row,
+                                                      int32_t *__restrict__ esc_col, int32_t *__restrict__ esc_val,
+                                                      int64_t cap, unsigned long long *__restrict__ n_esc) {
+    const int64_t words = (total + 3) >> 2;
+    for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < words; w += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t i0 = w << 2;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + j;
+            if (i >= total) break;
+            const uint32_t v = uint32_t(in[i]);
+            if (v > 254u) {                      // 255 marks an escaped entry (also the exact value 255)
+                const unsigned long long slot = atomicAdd(n_esc, 1ull);
+                if ((int64_t)slot < cap) {
+                    esc_row[slot] = int32_t(i / cols);
+                    esc_col[slot] = int32_t(i % cols);
+                    esc_val[slot] = int32_t(v);
+                }
+                packed |= 255u << (8 * j);
+            } else {
+                packed |= v << (8 * j);
+            }
+        }
+        if (i0 + 4 <= total) {
+            reinterpret_cast<uint32_t *>(out)[w] = packed;
+        } else {
+            for (int j = 0; i0 + j < total; ++j) out[i0 + j] = uint8_t(packed >> (8 * j));
+        }
+    }
+}
+
+// presence bits (kmerize.smk:112-120: vecs = counts > 0): bit (c & 7) of byte c >> 3 of a row of ceil(cols / 8) bytes
+// (numpy.unpackbits(..., bitorder="little")).  One warp per 32 columns of a row -> one ballot word.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_bits_kernel(const T *__restrict__ in, int64_t rows, int64_t cols, int64_t row_bytes,
+                                                        uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpr = (cols + 31) >> 5;                     // ballot words per row
+    const int64_t nw = rows * wpr;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t w = warp; w < nw; w += nwarps) {
+        const int64_t r = w / wpr, c = ((w - r * wpr) << 5) + lane;
+        const bool on = (c < cols) && in[r * cols + c] != T(0);
+        const unsigned m = __ballot_sync(FULL, on);
+        const int64_t byte0 = r * row_bytes + ((w - r * wpr) << 2);
+        if (lane < 4 && ((w - r * wpr) << 2) + lane < row_bytes) out[byte0 + lane] = uint8_t(m >> (8 * lane));
+    }
+}
+
+// rows of an int32 matrix with an element outside [lo, hi] (apply_tc: query counts that do not fit 8 bits)
+__global__ void __launch_bounds__(256) rows_out_of_range_kernel(const int32_t *__restrict__ X, int64_t rows, int64_t cols,
+                                                                int32_t lo, int32_t hi, int32_t *__restrict__ out,
+                                                                int64_t cap, unsigned long long *__restrict__ n_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        bool bad = false;
+        for (int64_t c = lane; c < cols; c += 32) {
+            const int32_t v = __ldg(X + r * cols + c);
+            bad |= (v < lo || v > hi);
+        }
+        if (__any_sync(FULL, bad) && lane == 0) {
+            const unsigned long long slot = atomicAdd(n_out, 1ull);
+            if ((int64_t)slot < cap) out[slot] = int32_t(r);
+        }
+    }
+}
+
 }  // namespace skm
 
 extern "C" {
@@ -109,6 +186,57 @@ int skm_scatter_add_i64(const int64_t *d_src, int64_t rows, int64_t cols, const 
     scatter_add_i64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, rows, cols, d_row_map, d_col_map,
                                                                   reinterpret_cast<unsigned long long *>(d_dst), dst_cols);
     SKM_LAUNCH_CHECK("scatter_add_i64_kernel");
+    return SKM_OK;
+}
+
+int skm_pack_counts_u8(const void *d_counts, int64_t rows, int64_t cols, int in_bits, uint8_t *d_out, int32_t *d_esc_row,
+                       int32_t *d_esc_col, int32_t *d_esc_val, int64_t esc_capacity, int64_t *d_n_esc, skm_stream_t stream) {
+    using namespace skm;
+    if (rows < 0 || cols < 0 || (in_bits != 32 && in_bits != 16) || esc_capacity < 0 || rows >= (1ll << 31) || cols >= (1ll << 31)) {
+        set_error("skm_pack_counts_u8: bad arguments (in_bits 32 or 16, rows / cols < 2^31)");
+        return SKM_ERR_INVALID;
+    }
+    if (!d_n_esc) { set_error("skm_pack_counts_u8: NULL d_n_esc"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_n_esc, 0, 8, st));
+    const int64_t total = rows * cols;
+    if (total == 0) return SKM_OK;
+    if (!d_counts || !d_out || (esc_capacity > 0 && (!d_esc_row || !d_esc_col || !d_esc_val))) { set_error("skm_pack_counts_u8: NULL argument"); return SKM_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) { set_error("skm_pack_counts_u8: d_out must be 4-byte aligned"); return SKM_ERR_INVALID; }
+    const int grid = (int)std::min<int64_t>(((total + 3) / 4 + 255) / 256, int64_t(sm_count()) * 16);
+    auto *n = reinterpret_cast<unsigned long long *>(d_n_esc);
+    if (in_bits == 32) pack_u8_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_counts, total, cols, d_out, d_esc_row, d_esc_col, d_esc_val, esc_capacity, n);
+    else pack_u8_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)d_counts, total, cols, d_out, d_esc_row, d_esc_col, d_esc_val, esc_capacity, n);
+    SKM_LAUNCH_CHECK("pack_u8_kernel");
+    return SKM_OK;
+}
+
+int skm_pack_presence_bits(const void *d_counts, int64_t rows, int64_t cols, int in_bits, uint8_t *d_out, skm_stream_t stream) {
+    using namespace skm;
+    if (rows < 0 || cols < 0 || (in_bits != 32 && in_bits != 16)) { set_error("skm_pack_presence_bits: bad arguments (in_bits 32 or 16)"); return SKM_ERR_INVALID; }
+    if (rows == 0 || cols == 0) return SKM_OK;
+    if (!d_counts || !d_out) { set_error("skm_pack_presence_bits: NULL argument"); return SKM_ERR_INVALID; }
+    const int64_t row_bytes = (cols + 7) >> 3;
+    const int64_t nw = rows * ((cols + 31) >> 5);
+    const int grid = (int)std::min<int64_t>((nw + 7) / 8, int64_t(sm_count()) * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_bits == 32) pack_bits_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_counts, rows, cols, row_bytes, d_out);
+    else pack_bits_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)d_counts, rows, cols, row_bytes, d_out);
+    SKM_LAUNCH_CHECK("pack_bits_kernel");
+    return SKM_OK;
+}
+
+int skm_rows_out_of_range_i32(const int32_t *d_X, int64_t rows, int64_t cols, int32_t lo, int32_t hi, int32_t *d_rows_out,
+                              int64_t capacity, int64_t *d_n_out, skm_stream_t stream) {
+    using namespace skm;
+    if (rows < 0 || cols < 0 || capacity < 0 || rows >= (1ll << 31) || !d_n_out) { set_error("skm_rows_out_of_range_i32: bad arguments"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, 8, st));
+    if (rows == 0 || cols == 0) return SKM_OK;
+    if (!d_X || (capacity > 0 && !d_rows_out)) { set_error("skm_rows_out_of_range_i32: NULL argument"); return SKM_ERR_INVALID; }
+    const int grid = (int)std::min<int64_t>((rows + 7) / 8, int64_t(sm_count()) * 16);
+    rows_out_of_range_kernel<<<grid, 256, 0, st>>>(d_X, rows, cols, lo, hi, d_rows_out, capacity, reinterpret_cast<unsigned long long *>(d_n_out));
+    SKM_LAUNCH_CHECK("rows_out_of_range_kernel");
     return SKM_OK;
 }
 

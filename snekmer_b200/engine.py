@@ -266,28 +266,59 @@ def kmer_totals(batch: SequenceBatch, alphabet: AlphabetT, k: int) -> torch.Tens
     return count
 
 
-def basis_finalize(alphabet: AlphabetT, k: int, count: torch.Tensor, first: torch.Tensor, min_filter: int = 0) -> Basis:
-    dev = count.device
+def basis_finalize(alphabet: AlphabetT, k: int, count: Optional[torch.Tensor], first: torch.Tensor, min_filter: int = 0) -> Basis:
+    """Tables -> basis in first-occurrence order.  count may be None (order-only tables, min_filter 0): every code
+    with a first position is kept and Basis.counts is None."""
+    dev = first.device
     tab = alphabet_tables(alphabet, dev)
-    S = count.numel()
+    S = first.numel()
     ws_bytes = lib().skm_basis_finalize_workspace(S)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     codes = torch.empty(S, dtype=torch.int64, device=dev)
-    counts = torch.empty(S, dtype=torch.int64, device=dev)
+    counts = torch.empty(S, dtype=torch.int64, device=dev) if count is not None else None
     col = torch.empty(S, dtype=torch.int32, device=dev)
     dK = torch.zeros(1, dtype=torch.int64, device=dev)
     check(lib().skm_basis_finalize(_ptr(count), _ptr(first), S, int(min_filter), _ptr(codes), _ptr(counts), _ptr(col),
                                    _ptr(dK), _ptr(ws), ws_bytes, _stream()))
     K = int(dK.item())
-    return Basis(tab.name, int(k), tab.symbols, codes[:K], counts[:K], col, K, S)
+    return Basis(tab.name, int(k), tab.symbols, codes[:K], None if counts is None else counts[:K], col, K, S)
 
 
-def build_basis(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0) -> Basis:
-    """Pass 1 of the vectorize rule (kmerize.smk:89-104) for one shard."""
+ORDER_FIRST_CHUNK_RES = 4 << 20     # residues in the first chunk of the order-only basis walk
+ORDER_GROWTH = 4                    # every further chunk is this many times longer
+
+
+def basis_first_progressive(batch: SequenceBatch, alphabet: AlphabetT, k: int, first: torch.Tensor, state: torch.Tensor,
+                            res_base: int = 0) -> None:
+    """first[c] = min(first[c], global position of the first window with code c), walking the shard front to back
+    and stopping on the device once every code of the space has been seen (state int32[4], zeroed by the caller)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    oh = np.ascontiguousarray(batch.offsets_host, dtype=np.int64)
+    check(lib().skm_basis_first_progressive(_ptr(batch.residues), batch.nres, _ptr(batch.offsets), oh.ctypes.data, batch.n,
+                                            _ptr(tab.lut), tab.nsym, int(k), int(res_base), _ptr(first), _ptr(state),
+                                            ORDER_FIRST_CHUNK_RES, ORDER_GROWTH, _stream()))
+
+
+def order_only_supported(S: int) -> bool:
+    return S <= lib().skm_basis_order_max_space()
+
+
+def build_basis(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: int = 0, counts: bool = True) -> Basis:
+    """Pass 1 of the vectorize rule (kmerize.smk:89-104) for one shard.
+
+    counts=False with min_filter <= 0 asks for the basis ORDER only (Basis.counts is None): the reference uses the
+    occurrence counts for nothing but the `count > min_filter` test, and with min_filter = 0 the basis is determined
+    by the first positions alone, so the walk stops as soon as every code of the space has been seen (small code
+    spaces; others take the full pass)."""
     tab = alphabet_tables(alphabet, batch.device)
     S = code_space(tab.nsym, k)
     if S > _native.SKM_DENSE_MAX_SPACE:
         raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    if not counts and min_filter <= 0 and order_only_supported(S):
+        first = torch.full((S,), -1, dtype=torch.int64, device=batch.device)
+        state = torch.zeros(4, dtype=torch.int32, device=batch.device)
+        basis_first_progressive(batch, alphabet, k, first, state, 0)
+        return basis_finalize(alphabet, k, None, first, 0)
     count, first = basis_tables(S, batch.device)
     basis_accumulate(batch, alphabet, k, count, first, 0)
     return basis_finalize(alphabet, k, count, first, min_filter)
@@ -513,6 +544,7 @@ class PreparedAnnotations:
     n_ann: int
     K: int
     mnorm2: torch.Tensor        # float64 [A]
+    M: Optional[torch.Tensor] = None    # the int64 matrix itself (a reference, not a copy): per-row fallback of apply_tc
 
     def tiles(self) -> np.ndarray:
         """The annotation tiles of the prepared matrix as int32 [n_tiles, 3] = (first sorted row, width, digit planes)
@@ -543,13 +575,27 @@ def prepare_annotations(M: torch.Tensor, mnorm2: Optional[torch.Tensor] = None) 
     if rc == -3:            # SKM_ERR_UNSUPPORTED: too many digit planes
         return None
     check(rc)
-    return PreparedAnnotations(planes, int(n_planes.value), A, K, row_norm2(M) if mnorm2 is None else mnorm2)
+    return PreparedAnnotations(planes, int(n_planes.value), A, K, row_norm2(M) if mnorm2 is None else mnorm2, M)
+
+
+def rows_out_of_range(X: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """Sorted indices (int64) of the rows of an int32 matrix that hold an element outside [lo, hi]."""
+    dev = _require_cuda(X.device)
+    X = X.contiguous()
+    rows, cols = X.shape
+    out = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+    dn = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_rows_out_of_range_i32(_ptr(X), rows, cols, int(lo), int(hi), _ptr(out), rows, _ptr(dn), _stream()))
+    n = int(dn.item())
+    return torch.sort(out[:n].to(torch.int64)).values
 
 
 def apply_tc(Q: torch.Tensor, prep: PreparedAnnotations, qnorm2: Optional[torch.Tensor] = None,
              full: bool = False) -> Optional[ApplyResult]:
-    """Tensor-core scoring (tcgen05 int8 GEMM, exact integer dots).  Returns None when a query
-    count exceeds 255 (the caller then uses the exact CUDA-core path)."""
+    """Tensor-core scoring (tcgen05 int8 GEMM, exact integer dots).  Query rows holding a count above 255 (a
+    5,000-residue low-complexity protein) do not fit the uint8 operand: they — and only they — are re-scored by the
+    exact CUDA-core path (skm_apply_dense) against prep.M.  Returns None only when such rows exist and the
+    prepared matrix does not carry M."""
     dev = _require_cuda(Q.device)
     Q = Q.contiguous()
     nq, K = Q.shape
@@ -568,7 +614,14 @@ def apply_tc(Q: torch.Tensor, prep: PreparedAnnotations, qnorm2: Optional[torch.
     check(lib().skm_apply_tc(_ptr(Q), nq, K, _ptr(prep.planes), prep.n_planes, A, _ptr(qnorm2), _ptr(prep.mnorm2), _ptr(top1),
                              _ptr(top2), _ptr(s1), _ptr(s2), _ptr(scores), _ptr(status), _ptr(ws), ws_bytes, _stream()))
     if int(status.item()) != 0:
-        return None
+        if prep.M is None:
+            return None
+        bad = rows_out_of_range(Q, 0, 255)
+        r = apply_dense(Q[bad].contiguous(), prep.M, qnorm2=qnorm2[bad].contiguous(), mnorm2=prep.mnorm2, full=full,
+                        tensor_cores=False)
+        top1[bad], top2[bad], s1[bad], s2[bad] = r.top1, r.top2, r.score1, r.score2
+        if full:
+            scores[bad] = r.scores
     return ApplyResult(top1, top2, s1, s2, scores)
 
 
@@ -853,15 +906,20 @@ def apply_sparse(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, c
     whether the exact integer dots fit 32-bit accumulators."""
     dev = _require_cuda(rowptr.device)
     nq = rowptr.numel() - 1
+    if nq == 0 or csc.n_ann == 0:               # no candidates: -1 / NaN, like apply_dense
+        return ApplyResult(torch.full((nq,), -1, dtype=torch.int32, device=dev), torch.full((nq,), -1, dtype=torch.int32, device=dev),
+                           torch.full((nq,), float("nan"), dtype=torch.float64, device=dev),
+                           torch.full((nq,), float("nan"), dtype=torch.float64, device=dev), None)
     top1 = torch.empty(nq, dtype=torch.int32, device=dev)
     top2 = torch.empty(nq, dtype=torch.int32, device=dev)
     s1 = torch.empty(nq, dtype=torch.float64, device=dev)
     s2 = torch.empty(nq, dtype=torch.float64, device=dev)
-    if nq == 0 or csc.n_ann == 0:
-        return ApplyResult(top1, top2, s1, s2, None)
     if max_row_total is None:
         max_row_total = query_row_total_max(rowptr, vals)
-    acc_bits = 32 if csc.max_m * max(int(max_row_total), 1) < 2 ** 32 else 64
+    acc_bits = sparse_acc_bits(csc.max_m, max_row_total)
+    if csc.n_ann > sparse_max_ann(acc_bits):
+        raise SkmError(-3, f"apply_sparse: {csc.n_ann} annotations with {acc_bits}-bit accumulators exceed one pass "
+                           f"({sparse_max_ann(acc_bits)}); use apply_sparse_tiled")
     check(lib().skm_apply_sparse(_ptr(rowptr), _ptr(cols), _ptr(vals), nq, _ptr(csc.colptr), _ptr(csc.rows), _ptr(csc.mvals),
                                  _ptr(csc.packed) if use_packed else None, _ptr(csc.mnorm2), _ptr(csc.inv_m32), csc.n_ann, acc_bits, _ptr(top1), _ptr(top2), _ptr(s1), _ptr(s2),
                                  None, _stream()))
@@ -877,16 +935,36 @@ def query_row_total_max(rowptr: torch.Tensor, vals: torch.Tensor) -> int:
     return int((csum[rowptr[1:]] - csum[rowptr[:-1]]).max().item())
 
 
-def apply_sparse_tiled(rowptr, cols, vals, keys, mvals, S: int, n_ann: int, tile: int = 8192) -> ApplyResult:
-    """All annotations of a sorted COO matrix, `tile` at a time, merged with the top-2 merge
-    (the same fan-in as the multi-GPU annotation sharding)."""
-    idxs, scs = [], []
+def sparse_acc_bits(max_m: int, max_row_total: int) -> int:
+    """Width of the exact integer accumulators of apply_sparse: a dot is at most max_m * (sum of the query's counts)."""
+    return 32 if int(max_m) * max(int(max_row_total), 1) < 2 ** 32 else 64
+
+
+def sparse_max_ann(acc_bits: int) -> int:
+    """Annotations one apply_sparse pass holds in shared memory (200 KB of accumulators)."""
+    return SPARSE_MAX_ANN if acc_bits == 32 else SPARSE_MAX_ANN // 2
+
+
+def apply_sparse_tiled(rowptr, cols, vals, keys, mvals, S: int, n_ann: int, tile: Optional[int] = None) -> ApplyResult:
+    """All annotations of a sorted COO matrix, `tile` at a time, merged with the top-2 merge (the same fan-in as the
+    multi-GPU annotation sharding).  The tile defaults to what one pass can hold, which depends on the accumulator
+    width: 51,200 annotations with 32-bit accumulators, 25,600 when max(M) * (largest query total) needs 64 bits."""
+    dev = rowptr.device
+    nq = rowptr.numel() - 1
+    if n_ann <= 0 or nq <= 0:
+        return ApplyResult(torch.full((nq,), -1, dtype=torch.int32, device=dev), torch.full((nq,), -1, dtype=torch.int32, device=dev),
+                           torch.full((nq,), float("nan"), dtype=torch.float64, device=dev),
+                           torch.full((nq,), float("nan"), dtype=torch.float64, device=dev), None)
     row_total = query_row_total_max(rowptr, vals)
-    for a0 in range(0, max(n_ann, 1), tile):
+    max_m = int(mvals.max().item()) if mvals.numel() else 0
+    cap = sparse_max_ann(sparse_acc_bits(max_m, row_total))
+    tile = cap if tile is None else max(1, min(int(tile), cap))
+    idxs, scs = [], []
+    for a0 in range(0, n_ann, tile):
         na = min(tile, n_ann - a0)
-        if na <= 0:
-            break
         r = apply_sparse(rowptr, cols, vals, csc_build(keys, mvals, S, na, a0), row_total)
+        if n_ann <= tile:
+            return r
         i = torch.stack([r.top1.to(torch.int64), r.top2.to(torch.int64)])
         idxs.append(torch.where(i >= 0, i + a0, i))
         scs.append(torch.stack([r.score1, r.score2]))

@@ -42,17 +42,38 @@ INDEX_COL = "__index_level_0__"
 # ---------------------------------------------------------------------------
 # vectorize
 # ---------------------------------------------------------------------------
+DENSE_MAX_K = 51200         # widest basis the dense kernels hold (a 200 KB shared-memory row of int32 counters)
+VECS_MAX_BYTES = 32 << 30   # largest float64 presence matrix vecs() will materialise on the host
+
+
+def _dense_envelope_error(what: str, K: int) -> E.SkmError:
+    return E.SkmError(-3, f"{what}: a basis of {K} k-mers is outside the dense envelope of the rule bodies (K <= {DENSE_MAX_K}); "
+                          "the reference's dense CSV / matrix layout does not scale there either — use the sparse rule bodies "
+                          "snekmer_b200.rules_sparse.learn_counts_sparse / merge_counts_sparse / apply_counts_sparse with the "
+                          ".skmc / .skmv side-cars (sidecar.py)")
+
+
 @dataclass
 class VectorizeResult:
     kmerlist: np.ndarray        # '<Uk' [K] (or the supplied list)
     ids: List[str]
     seqs: List[str]             # reduced sequences (trailing '*' removed)
     lengths: np.ndarray         # raw lengths, int64 [N]
-    counts: torch.Tensor        # device int32 [N, K]; vecs = counts > 0
+    counts: Optional[torch.Tensor]      # device int32 [N, K]; vecs = counts > 0 (None when the basis is too wide: see csr)
+    csr: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None   # (rowptr int64 [N+1], cols int32 [nnz], vals int32 [nnz])
 
     def vecs(self) -> np.ndarray:
         """float64 0/1 presence matrix, as the rule stores it (kmerize.smk:112-120)."""
-        return (self.counts > 0).to(torch.float64).cpu().numpy()
+        if self.counts is not None:
+            return (self.counts > 0).to(torch.float64).cpu().numpy()
+        n, K = len(self.ids), len(self.kmerlist)
+        if n * K * 8 > VECS_MAX_BYTES:
+            raise MemoryError(f"the dense float64 presence matrix of this shard is {n} x {K} ({n * K * 8 / 2 ** 30:.0f} GiB); "
+                              "write the CSR side-car instead (vectorize_rule(out_npz=None, out_sidecar=...))")
+        rowptr, cols, _ = (t.cpu().numpy() for t in self.csr)
+        out = np.zeros((n, K), dtype=np.float64)
+        out[np.repeat(np.arange(n), np.diff(rowptr)), cols] = 1.0
+        return out
 
     def write_sidecar(self, path: str, alphabet, k: int) -> None:
         """Binary side-car (.skmv, sidecar.py) of this shard: COUNTS as CSR instead of the dense float64 presence
@@ -64,6 +85,11 @@ class VectorizeResult:
         symbols = _alpha.symbols(name)
         codes, ok = E.encode_kmers([str(x) for x in self.kmerlist], symbols, k)
         assert bool(ok.all()), "a k-mer of the basis does not belong to the alphabet"
+        if self.counts is None:
+            rowptr, cols, vals = self.csr
+            sidecar.write_vectors(path, name, k, symbols, codes, self.ids, self.seqs, self.lengths, rowptr.cpu().numpy(),
+                                  cols.to(torch.int32).cpu().numpy(), vals.to(torch.int32).cpu().numpy())
+            return
         nz = self.counts.nonzero()
         rowptr = torch.zeros(self.counts.shape[0] + 1, dtype=torch.int64, device=self.counts.device)
         if nz.numel():
@@ -92,14 +118,26 @@ def vectorize_packed(ids: Sequence[str], residues: np.ndarray, offsets: np.ndarr
     Python objects on the way to the device."""
     batch = E.SequenceBatch.from_packed(residues, offsets, pinned=pinned)
     lengths = np.diff(np.asarray(offsets, dtype=np.int64))
+    csr = None
     if kmerbasis is not None:                       # basis.txt branch, kmerize.smk:72-78
         kmerlist = list(kmerbasis)
+        if len(kmerlist) > DENSE_MAX_K:
+            raise _dense_envelope_error("vectorize with a basis file", len(kmerlist))
         counts = E.count_over_kmers(batch, alphabet, k, kmerlist)
     else:                                           # kmerize.smk:85-104
-        basis = E.build_basis(batch, alphabet, k, min_filter)
+        tab = E.alphabet_tables(alphabet, batch.device)
+        if E.code_space(tab.nsym, k) <= E._native.SKM_DENSE_MAX_SPACE:
+            # the occurrence counts only serve the `count > min_filter` test: without a filter the basis ORDER is enough
+            basis = E.build_basis(batch, alphabet, k, min_filter, counts=min_filter > 0)
+            if basis.K <= DENSE_MAX_K:
+                counts = E.count_dense(batch, alphabet, k, basis)
+            else:                                   # too wide for dense rows: CSR over the basis columns
+                counts, csr = None, E.count_csr(batch, alphabet, k, basis)
+        else:                                       # code spaces beyond 2^27: sort-based basis, CSR counts
+            v = E.vectorize(batch, alphabet, k, min_filter)
+            basis, counts, csr = v.basis, None, (v.rowptr, v.cols, v.vals)
         kmerlist = basis.kmers() if basis.K else np.array([])
-        counts = E.count_dense(batch, alphabet, k, basis)
-    return VectorizeResult(kmerlist, list(ids), _reduced_strings(batch, alphabet), lengths, counts)
+    return VectorizeResult(kmerlist, list(ids), _reduced_strings(batch, alphabet), lengths, counts, csr)
 
 
 def vectorize_rule(fasta: str, out_npz: Optional[str], out_kmerobj: Optional[str], alphabet, k: int, min_filter: int = 0,
@@ -157,6 +195,8 @@ def learn_counts(ids: Sequence[str], reduced_seqs: Sequence[str], kmerlist: Sequ
     its LAST counts, while every copy has already been added to the totals.  Annotation
     rows appear in the order their first (distinct) sequence does."""
     kmerlist = [str(x) for x in kmerlist]
+    if len(kmerlist) > DENSE_MAX_K:
+        raise _dense_envelope_error("learn", len(kmerlist))
     tab, k = _kmer_tables(kmerlist)
     batch = E.SequenceBatch.from_strings([str(s) for s in reduced_seqs])
     last = {}
@@ -326,6 +366,8 @@ def cosine_top2(reduced_seqs: Sequence[str], query_kmers: Sequence[str], totals:
     their k-mer columns, so the query norm runs over the query file's own k-mer list while
     the dot product only sees k-mers present in both lists."""
     query_kmers = [str(x) for x in query_kmers]
+    if max(len(query_kmers), len(totals.kmers)) > DENSE_MAX_K:
+        raise _dense_envelope_error("apply", max(len(query_kmers), len(totals.kmers)))
     keep = [i for i, r in enumerate(totals.rows) if r != "Totals"]
     M = torch.from_numpy(np.ascontiguousarray(totals.M[keep])).to(E._require_cuda())
     tab, k = _kmer_tables(query_kmers, totals.kmers) if totals.kmers else _kmer_tables(query_kmers)

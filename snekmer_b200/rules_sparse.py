@@ -166,20 +166,39 @@ def merge_counts_sparse(parts: Sequence[SparseCounts]) -> SparseCounts:
     return SparseCounts(list(index), seq_count, parts[0].symbols, parts[0].k, keys, vals, totals, total_seqs)
 
 
+def restrict_csr_to_kmers(rowptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, symbols: str, k: int,
+                          kmers: Sequence[str]):
+    """Drop the CSR entries (codes) that are not in `kmers` — the query file's own kmerlist: the reference takes the
+    query norm over that list only (apply.smk:262-289), which matters when the vectorize step ran with min_filter > 0 or
+    a basis.txt."""
+    S = len(symbols) ** int(k)
+    codes, ok = E.encode_kmers([str(x) for x in kmers], symbols, int(k))
+    member = torch.zeros(S, dtype=torch.bool, device=cols.device)
+    member[torch.from_numpy(codes[ok].astype(np.int64)).to(cols.device)] = True
+    keep = member[cols.to(torch.int64)]
+    csum = torch.zeros(keep.numel() + 1, dtype=torch.int64, device=cols.device)
+    torch.cumsum(keep, 0, out=csum[1:])
+    return csum[rowptr], cols[keep].contiguous(), vals[keep].contiguous()
+
+
 def apply_counts_sparse(ids: Sequence[str], reduced_seqs: Sequence[str], sc: SparseCounts, confidence_csv: Optional[str] = None,
-                        out_summary: Optional[str] = None, tile: int = E.SPARSE_MAX_ANN) -> ScoreResult:
+                        out_summary: Optional[str] = None, tile: Optional[int] = None,
+                        query_kmers: Optional[Sequence[str]] = None) -> ScoreResult:
     """KmerCompare of the apply workflow (apply.smk:224-342) as SpMM: cosine of every query against every annotation
-    row, top-2, delta, Confidence; writes kmer-summary CSV when asked.  A repeated id keeps its last record."""
+    row, top-2, delta, Confidence; writes kmer-summary CSV when asked.  A repeated id keeps its last record.
+    query_kmers: the query file's kmerlist (from its .npz / side-car).  The reference's query norm and dot run over that
+    list; without it every valid window of the query counts — the same thing when the vectorize step ran with
+    min_filter = 0 and no basis file, which is the only case the two differ in.  The annotation tile follows the
+    accumulator width the data needs (engine.apply_sparse_tiled)."""
     uniq, pick = _unique_last(list(ids))
     seqs = [str(reduced_seqs[int(i)]) for i in pick]
     tab = E.alphabet_tables_from_symbols(sc.symbols)
     batch = E.SequenceBatch.from_strings(seqs)
     rowptr, cols, cvals = E.count_csr(batch, tab, sc.k, None)
+    if query_kmers is not None:
+        rowptr, cols, cvals = restrict_csr_to_kmers(rowptr, cols, cvals, tab.symbols, sc.k, query_kmers)
     A = len(sc.annotations)
-    if A <= tile:
-        r = E.apply_sparse(rowptr, cols, cvals, E.csc_build(sc.keys, sc.vals, sc.S, A, 0))
-    else:
-        r = E.apply_sparse_tiled(rowptr, cols, cvals, sc.keys, sc.vals, sc.S, A, tile)
+    r = E.apply_sparse_tiled(rowptr, cols, cvals, sc.keys, sc.vals, sc.S, A, tile)
     top1, top2 = r.top1.cpu().numpy(), r.top2.cpu().numpy()
     s1, s2 = r.score1.cpu().numpy(), r.score2.cpu().numpy()
     if out_summary:

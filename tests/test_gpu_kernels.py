@@ -381,6 +381,9 @@ def test_apply_tensor_cores_envelope_fallbacks():
     Q[3, 7] = 300                                        # does not fit 8 bits -> exact path
     M = torch.ones((5, 64), dtype=torch.int64).cuda()
     prep = E.prepare_annotations(M)
+    rt = E.apply_tc(Q, prep)                             # row 3 alone is re-scored by the exact path
+    assert rt is not None and rt.top1[3].item() == 0 and abs(rt.score1[3].item() - 300 / (300 * 8.0)) < 1e-15
+    prep.M = None                                        # a prepared matrix without M cannot re-score: None
     assert E.apply_tc(Q, prep) is None
     r = E.apply_dense(Q, M, tensor_cores=True)
     assert r.top1[3].item() == 0 and abs(r.score1[3].item() - 300 / (300 * 8.0)) < 1e-15

@@ -1,0 +1,264 @@
+"""GPU parity tests added in round 2: order-only basis walk with device-side early exit, per-row fallback of the
+tensor-core scoring, compact count transports, host pipelines."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import skm_oracle as O
+from snekmer_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+AA = np.array(list("ACDEFGHIKLMNPQRSTVWYX"))
+
+
+def _rand_seqs(rng, n, lo, hi, p_x=0.02):
+    p = np.full(21, (1 - p_x) / 20)
+    p[-1] = p_x
+    return ["".join(rng.choice(AA, size=int(rng.integers(lo, hi)), p=p)) for _ in range(n)]
+
+
+def _oracle_basis(seqs, a, k, mf=0):
+    lut, syms = O.build_lut(a)
+    res, offs = O.pack(seqs)
+    si, pos, code, valid = O.window_codes(res, offs, lut, len(syms), k)
+    basis, cnt = O.basis_codes(si, pos, code, valid, mf)
+    return basis, cnt, (si, code, valid)
+
+
+@pytest.mark.parametrize("a,k,n,first_chunk", [("miqs", 3, 3000, 1 << 12), ("miqs", 3, 3000, 1 << 30), (2, 8, 4000, 1 << 14),
+                                               (0, 9, 2500, 1 << 10), ("standard", 4, 500, 1 << 9), (None, 3, 1500, 1 << 13)])
+def test_order_only_basis_equals_full_basis(a, k, n, first_chunk, monkeypatch):
+    """build_basis(counts=False): same basis (order included) as the full pass and as the oracle, whether the space
+    saturates in the first chunk, in a later one, or never."""
+    rng = np.random.default_rng(k * 100 + n)
+    seqs = _rand_seqs(rng, n, 0, 300)
+    seqs[5] = ""
+    batch = E.SequenceBatch.from_strings(seqs)
+    want, _, _ = _oracle_basis(seqs, a, k)
+    monkeypatch.setattr(E, "ORDER_FIRST_CHUNK_RES", first_chunk)
+    monkeypatch.setattr(E, "ORDER_GROWTH", 2)
+    b = E.build_basis(batch, a, k, 0, counts=False)
+    assert b.counts is None
+    assert np.array_equal(b.codes_host(), want)
+    full = E.build_basis(batch, a, k, 0)
+    assert torch.equal(full.codes, b.codes) and torch.equal(full.col_of_code, b.col_of_code)
+    C = E.count_dense(batch, a, k, b)
+    assert torch.equal(C.sum(dim=0, dtype=torch.int64), full.counts)
+
+
+def test_order_only_basis_early_exit_state():
+    """The walk really stops: a saturated space leaves state[0] = 1 and first positions inside the scanned prefix;
+    k-mers that only occur at the very end are still found when the space never saturates."""
+    rng = np.random.default_rng(7)
+    seqs = _rand_seqs(rng, 6000, 50, 300, p_x=0.0)
+    batch = E.SequenceBatch.from_strings(seqs)
+    tab = E.alphabet_tables("hydro", batch.device)       # 2 letters, k = 4: 16 codes, saturated within a few residues
+    S = tab.nsym ** 4
+    first = torch.full((S,), -1, dtype=torch.int64, device=batch.device)
+    state = torch.zeros(4, dtype=torch.int32, device=batch.device)
+    old = E.ORDER_FIRST_CHUNK_RES
+    try:
+        E.ORDER_FIRST_CHUNK_RES = 1 << 12
+        E.basis_first_progressive(batch, "hydro", 4, first, state, 0)
+    finally:
+        E.ORDER_FIRST_CHUNK_RES = old
+    st = state.cpu().numpy()
+    assert st[0] == 1 and st[2] == S and st[1] == 0
+    assert int(first.max().item()) < (1 << 12) + 400
+    # rare k-mer at the end of the shard: 'W' only in the last sequence (None alphabet, k = 2 -> WW)
+    seqs2 = ["".join(rng.choice(AA[:18], size=200)) for _ in range(3000)] + ["AWWA"]
+    b2 = E.build_basis(E.SequenceBatch.from_strings(seqs2), None, 2, 0, counts=False)
+    want, _, _ = _oracle_basis(seqs2, None, 2)
+    assert np.array_equal(b2.codes_host(), want)
+
+
+def test_apply_tc_per_row_fallback_long_homopolymer():
+    """One 60k-residue homopolymer (a count of ~60,000 in one column) inside a large batch: only that row leaves the
+    tensor-core path; every row equals the exact CUDA-core result bit for bit."""
+    rng = np.random.default_rng(3)
+    a, k = "miqs", 3
+    seqs = _rand_seqs(rng, 20000, 30, 400)
+    seqs[777] = "A" * 60000
+    seqs[12345] = "L" * 300 + "".join(rng.choice(AA[:20], size=100))          # a count of 298: just over 255
+    batch = E.SequenceBatch.from_strings(seqs)
+    Q = E.count_dense(batch, a, k, None)
+    M = torch.from_numpy(rng.integers(0, 50, size=(300, Q.shape[1]), dtype=np.int64) * (rng.random((300, Q.shape[1])) < 0.4)).cuda()
+    prep = E.prepare_annotations(M)
+    bad = E.rows_out_of_range(Q, 0, 255)
+    assert bad.tolist() == [777, 12345]
+    tc = E.apply_tc(Q, prep)
+    exact = E.apply_dense(Q, M, tensor_cores=False)
+    assert torch.equal(tc.top1, exact.top1) and torch.equal(tc.top2, exact.top2)
+    assert torch.allclose(tc.score1, exact.score1, rtol=1e-14, atol=0) and torch.allclose(tc.score2, exact.score2, rtol=1e-14, atol=0)
+    assert torch.equal(tc.score1[bad], exact.score1[bad])
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.uint16])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (37, 1000), (200, 6561), (513, 27), (64, 3)])
+def test_pack_counts_u8_and_presence_bits(dtype, rows, cols):
+    from snekmer_b200 import pipeline as P
+
+    rng = np.random.default_rng(rows * cols)
+    X = (rng.integers(0, 40, size=(rows, cols)) * (rng.random((rows, cols)) < 0.3)).astype(np.int64)
+    X[rng.integers(0, rows), rng.integers(0, cols)] = 255
+    X[rng.integers(0, rows), rng.integers(0, cols)] = 254
+    X[rng.integers(0, rows), rng.integers(0, cols)] = 60000
+    X[0, 0] = 256
+    d = torch.from_numpy(X.astype(np.int32)).cuda().to(dtype) if dtype == torch.int32 else torch.from_numpy(X.astype(np.uint16)).cuda()
+    u8, er, ec, evv = P.pack_counts_u8(d)
+    got = P.unpack_counts_u8(u8.cpu().numpy(), er.cpu().numpy(), ec.cpu().numpy(), evv.cpu().numpy())
+    assert np.array_equal(got, X)
+    assert int((u8 == 255).sum().item()) == er.numel() == int((X >= 255).sum())
+    bits = P.pack_presence_bits(d)
+    assert tuple(bits.shape) == (rows, (cols + 7) // 8)
+    assert np.array_equal(np.unpackbits(bits.cpu().numpy(), axis=1, bitorder="little")[:, :cols], (X > 0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("transport", ["int32", "uint16", "uint8", "bits"])
+def test_vectorize_host_transports_match_oracle(transport):
+    from snekmer_b200 import pipeline as P
+
+    rng = np.random.default_rng(11)
+    seqs = _rand_seqs(rng, 5000, 0, 500)
+    seqs[17] = "G" * 1000                                                  # a count of 998 -> escape list of the uint8 transport
+    a, k = "miqs", 3
+    res, offs = E.SequenceBatch.pack_host(seqs)
+    want_basis, _, (si, code, valid) = _oracle_basis(seqs, a, k)
+    want = O.count_matrix(si, code, valid, len(seqs), want_basis)
+    h_res = torch.from_numpy(res.copy()).pin_memory()
+    r = P.vectorize_host(h_res, offs, a, k, transport=transport, n_chunks=5)
+    assert np.array_equal(r.basis.codes_host(), want_basis)
+    if transport == "bits":
+        assert np.array_equal(r.presence(), (want > 0))
+    else:
+        assert np.array_equal(r.counts(), want)
+        assert r.counts().dtype == np.int32
+
+
+def test_apply_host_matches_device_path():
+    from snekmer_b200 import pipeline as P
+
+    rng = np.random.default_rng(5)
+    a, k = "miqs", 3
+    train = _rand_seqs(rng, 3000, 30, 300)
+    ann = rng.integers(0, 200, size=len(train)).astype(np.int32)
+    tb = E.SequenceBatch.from_strings(train)
+    M, _ = E.learn_dense(tb, a, k, None, torch.from_numpy(ann), 200)
+    M = M[:200].contiguous()
+    prep = E.prepare_annotations(M)
+    queries = _rand_seqs(rng, 7000, 0, 400)
+    queries[3] = "A" * 3000
+    res, offs = E.SequenceBatch.pack_host(queries)
+    h = P.apply_host(torch.from_numpy(res.copy()).pin_memory(), offs, a, k, prep, n_chunks=3)
+    qb = E.SequenceBatch.from_strings(queries)
+    Q = E.count_dense(qb, a, k, None)
+    want = E.apply_dense(Q, M, tensor_cores=False)
+    assert np.array_equal(h.top1, want.top1.cpu().numpy()) and np.array_equal(h.top2, want.top2.cpu().numpy())
+    assert np.allclose(h.score1, want.score1.cpu().numpy(), rtol=1e-14, atol=0)
+    assert np.allclose(h.score2, want.score2.cpu().numpy(), rtol=1e-14, atol=0)
+    S = O.cosine_scores(Q.cpu().numpy(), M.cpu().numpy())
+    i1, _, s1, _ = O.top2(S)
+    assert np.array_equal(h.top1, i1) and np.max(np.abs(h.score1 - s1)) < 1e-12
+
+
+def test_apply_sparse_64bit_accumulators_with_many_annotations():
+    """more than 25,600 annotations AND dots that need 64-bit accumulators (max(M) * query total >= 2^32):
+    the annotation tile follows the accumulator width; results equal the dense float64 oracle."""
+    rng = np.random.default_rng(64)
+    a, k = "hydro", 10                                   # 2 letters: S = 1024
+    S, n_ann = 1024, 30000
+    nnz = 200000
+    ann = np.sort(rng.integers(0, n_ann, size=nnz))
+    code = rng.integers(0, S, size=nnz)
+    key = np.unique(ann.astype(np.int64) * S + code)
+    val = rng.integers(1, 50, size=key.size).astype(np.int64)
+    val[5] = 70000                                       # >= 65536: unpacked CSC, and 70000 * 70000 >= 2^32
+    keys, vals = torch.from_numpy(key).cuda(), torch.from_numpy(val).cuda()
+    queries = _rand_seqs(rng, 300, 0, 300, p_x=0.0) + ["".join(rng.choice(list("AV"), size=70100))]
+    qb = E.SequenceBatch.from_strings(queries)
+    rowptr, cols, cvals = E.count_csr(qb, a, k, None)
+    row_total = E.query_row_total_max(rowptr, cvals)
+    assert E.sparse_acc_bits(70000, row_total) == 64 and E.sparse_max_ann(64) < n_ann
+    with pytest.raises(E.SkmError):
+        E.apply_sparse(rowptr, cols, cvals, E.csc_build(keys, vals, S, n_ann, 0), row_total)
+    r = E.apply_sparse_tiled(rowptr, cols, cvals, keys, vals, S, n_ann)
+    lut, syms = O.build_lut(a)
+    res, offs = O.pack(queries)
+    si, pos, codes, valid = O.window_codes(res, offs, lut, len(syms), k)
+    Q = O.count_matrix(si, codes, valid, len(queries), np.arange(S, dtype=np.uint64))
+    M = np.zeros((n_ann, S), dtype=np.int64)
+    M[key // S, key % S] = val
+    Sc = O.cosine_scores(Q, M)
+    i1, i2, s1, s2 = O.top2(Sc)
+    assert np.allclose(r.score1.cpu().numpy(), s1, rtol=1e-12, atol=1e-15) and np.allclose(r.score2.cpu().numpy(), s2, rtol=1e-12, atol=1e-15)
+    clear = (s1 - s2) > 1e-12 * np.maximum(s1, 1e-30)
+    assert np.array_equal(r.top1.cpu().numpy()[clear], i1[clear])
+    # empty inputs give -1 / NaN on both sparse entry points
+    e = E.apply_sparse_tiled(rowptr, cols, cvals, keys[:0], vals[:0], S, 0)
+    assert int(e.top1.max().item()) == -1 and bool(torch.isnan(e.score1).all())
+
+
+def test_apply_counts_sparse_query_kmerlist_restriction():
+    """with the query file's kmerlist (min_filter > 0) the sparse rule's norm runs over that list only, like
+    the dense rule and the reference (apply.smk:262-289)."""
+    from snekmer_b200 import rules as R
+    from snekmer_b200 import rules_sparse as RS
+
+    rng = np.random.default_rng(9)
+    a, k = 2, 4
+    ids = [f"tr|T{i:04d}|x" for i in range(400)]
+    seqs = _rand_seqs(rng, 400, 20, 200, p_x=0.0)
+    ann = {f"T{i:04d}": f"FAM{int(rng.integers(0, 9))}" for i in range(400) if rng.random() < 0.8}
+    red = [O.reduce_str(s, a) for s in seqs]
+    syms = "".join(sorted(O.symbols_of(a)))
+    sc = RS.learn_counts_sparse(ids, red, syms, k, ann)
+    q_ids = [f"tr|Q{i:04d}|y" for i in range(150)]
+    q_seqs = _rand_seqs(rng, 150, 10, 200, p_x=0.0)
+    q_red = [O.reduce_str(s, a) for s in q_seqs]
+    qb = E.SequenceBatch.from_strings(q_seqs)
+    q_basis = E.build_basis(qb, a, k, 3)                                    # min_filter = 3 drops rare k-mers
+    q_kmers = list(q_basis.kmers())
+    assert 0 < len(q_kmers) < len(syms) ** k
+    all_kmers = list(E.decode_kmers(np.arange(len(syms) ** k, dtype=np.uint64), syms, k))
+    lr = R.learn_counts(ids, red, all_kmers, ann)
+    table = R.CountsTable(["Totals"] + lr.annotations, all_kmers, np.concatenate([[lr.total_seqs], lr.seq_count]),
+                          np.concatenate([[lr.totals.sum()], lr.M.sum(axis=1)]), np.concatenate([lr.totals[None], lr.M]))
+    want = R.cosine_top2(q_red, q_kmers, table)
+    got = RS.apply_counts_sparse(q_ids, q_red, sc, query_kmers=q_kmers)
+    assert got.annotations == lr.annotations
+    assert np.allclose(got.score1, want.score1.cpu().numpy(), rtol=1e-12, atol=1e-15)
+    assert np.allclose(got.score2, want.score2.cpu().numpy(), rtol=1e-12, atol=1e-15)
+    loose = RS.apply_counts_sparse(q_ids, q_red, sc)                        # without the list: norm over all windows
+    assert not np.allclose(loose.score1, got.score1)
+
+
+@pytest.mark.parametrize("a,k,n", [(None, 4, 300), (None, 8, 200)])
+def test_vectorize_rule_beyond_the_dense_envelope(a, k, n, tmp_path):
+    """the vectorize rule body no longer hard-fails when the basis has more than 51,200 k-mers (table space,
+    CSR counts) or the code space exceeds 2^27 (sort-based wide path): same kmerlist / presence matrix as the oracle;
+    learn / apply on such a basis name the sparse rule bodies."""
+    from snekmer_b200 import rules as R
+
+    rng = np.random.default_rng(k)
+    seqs = _rand_seqs(rng, n, 100, 500, p_x=0.01)
+    ids = [f"tr|W{i:04d}|w" for i in range(n)]
+    r = R.vectorize_records(ids, seqs, a, k)
+    want_basis, _, (si, code, valid) = _oracle_basis(seqs, a, k)
+    lut, syms = O.build_lut(a)
+    assert r.counts is None and r.csr is not None and len(r.kmerlist) == len(want_basis) > R.DENSE_MAX_K
+    assert list(r.kmerlist) == list(O.decode(want_basis, syms, k))
+    C = O.count_matrix(si, code, valid, n, want_basis)
+    assert np.array_equal(r.vecs(), (C > 0).astype(np.float64))
+    rowptr, cols, vals = (t.cpu().numpy() for t in r.csr)
+    dense = np.zeros_like(C)
+    dense[np.repeat(np.arange(n), np.diff(rowptr)), cols] = vals
+    assert np.array_equal(dense, C)
+    side = str(tmp_path / "w.skmv")
+    r.write_sidecar(side, a, k)
+    from snekmer_b200 import sidecar as SC
+    SC.export_npz(side, str(tmp_path / "w.npz"))
+    z = np.load(str(tmp_path / "w.npz"))
+    assert list(z["kmerlist"]) == list(r.kmerlist) and np.array_equal(z["vecs"], r.vecs())
+    with pytest.raises(E.SkmError, match="rules_sparse"):
+        R.learn_counts(ids, r.seqs, list(r.kmerlist), {})
