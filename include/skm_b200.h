@@ -377,6 +377,12 @@ SKM_API int skm_pack_presence_bits(const void *d_counts, int64_t rows, int64_t c
 SKM_API int skm_rows_out_of_range_i32(const int32_t *d_X, int64_t rows, int64_t cols, int32_t lo, int32_t hi,
                               int32_t *d_rows_out, int64_t capacity, int64_t *d_n_out, skm_stream_t stream);
 
+/* Measurement helper (not on the product path): a kernel of `blocks` x 256 threads, each running 16 independent
+ * chains of `iters` fp32 FMAs; *flops_out (host) = the flops it executes.  Timed with CUDA events by
+ * scripts/measure_peaks.py it gives the fp32-FMA peak the sparse scoring roofline is quoted against.
+ * d_out: float [blocks * 256] (never written in practice). */
+SKM_API int skm_bench_fma_f32(int64_t iters, int blocks, float *d_out, double *flops_out, skm_stream_t stream);
+
 /* (a11) per-sequence counts as CSR WITHOUT a device-wide sort: a warp scans one sequence, sorts its window keys in
  * shared memory (bitonic network) and run-length encodes them; longer sequences get a CTA.  Same results as
  * skm_count_csr (key_bits = 32: keys = codes, or basis columns when d_col_of_code [S] is given; rows sorted by key)

@@ -91,6 +91,7 @@ SIGNATURES = {
     "skm_pack_counts_u8": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _i64, _p, _p]),
     "skm_pack_presence_bits": (_int, [_p, _i64, _i64, _int, _p, _p]),
     "skm_rows_out_of_range_i32": (_int, [_p, _i64, _i64, C.c_int32, C.c_int32, _p, _i64, _p, _p]),
+    "skm_bench_fma_f32": (_int, [_i64, _int, _p, C.POINTER(C.c_double), _p]),
     "skm_scatter_add_i64": (_int, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _p]),
 }
 
