@@ -154,7 +154,23 @@ constexpr int CW_SYM = ts_sym_bytes(CW_SEG);      // 480
 // symbols are used raw (an invalid symbol's garbage digit is added and later subtracted with the same value, and no
 // window containing it is ever emitted), and the column comes from shared memory: 13 SASS instructions per residue
 // against 24 for the generic scanner.
+// WORDS (k - 1 <= 4, i.e. every dense basis of practical size): the scan reads its symbols as aligned 32-bit words —
+// a lane owns a 4-aligned chunk, keeps the previous word in a register and gets the four symbols that LEAVE the
+// window from one funnel shift of (previous : current) — instead of two LDS.U8 per residue, and it needs no run
+// counter: a word whose 4 symbols and the k-1 symbols in front of it are all valid (99.4 % of them) emits its four
+// windows unconditionally; the others (sequence start, X / B / Z ...) test each window against the invalid-byte mask
+// of the (previous : current) pair.  Measured on C2: 700 -> ~490 warp instructions and 221 -> ~190 shared wavefronts
+// per sequence (profiles/R2*).
 template <typename OutT, int MAP>
+__device__ __forceinline__ void cw_emit(uint32_t code, uint32_t cnt_addr, uint32_t col_addr, const int32_t *__restrict__ col_of_code, int K) {
+    uint32_t col;
+    if (MAP == 0) col = code;
+    else if (MAP == 1) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(col) : "r"(col_addr + 2u * code));
+    else { const int32_t c = __ldg(col_of_code + code); col = c >= 0 ? uint32_t(c) : uint32_t(K); }
+    cnt_ops<OutT>::add(cnt_addr, col);
+}
+
+template <typename OutT, int MAP, bool WORDS>
 __global__ void __launch_bounds__(32 * CW_WARPS, 6)
 count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
                         const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
@@ -188,6 +204,12 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     const uint32_t uk = uint32_t(k);
+    const uint32_t km1 = uk - 1u;
+    // WORDS: shift that turns (previous : current) into the word of outgoing symbols, mask of the k-1 bytes of the
+    // previous word a window of this word can reach into, and the k-bit window mask over the pair's 8 validity bits
+    const uint32_t out_shift = 32u - 8u * km1;
+    const uint32_t prev_mask = km1 ? (0xC0C0C0C0u << (out_shift & 31u)) : 0u;
+    const uint32_t win_bits = (1u << uk) - 1u;
     int64_t e = (lo < hi) ? __ldg(off + lo) : 0;
     for (int64_t s = lo; s < hi; ++s) {
         const int64_t b = e;
@@ -224,35 +246,76 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
             __syncwarp();
             if (first) {                                    // nothing in front of the sequence start is a residue of it
                 for (int i = lane; i < lo_i; i += 32) s_sym[i] = uint8_t(SYM_BAD);
-                __syncwarp();
             }
-            // scan: lane owns symbols [i0, i1), warms up on the k-1 symbols in front of them
-            const int n = hi_i - lo_i;
-            const int C = ((((n + 31) >> 5) + 3) >> 2 | 1) << 2;     // smallest 4 * odd >= ceil(n / 32)
-            const int i0 = lo_i + lane * C, i1 = min(i0 + C, hi_i);
-            if (i0 < i1) {
-                uint32_t run = 0, code = 0;
-                uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
-                for (uint32_t j = 1; j < uk; ++j, ++p) {
-                    const uint32_t sy = lds_u8<0>(p);
-                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
-                    code = code * nsym + sy;
-                }
-                const uint32_t pend = sym_addr + uint32_t(i1);
-                const uint32_t back = uk - 1u;
-#pragma unroll 4
-                for (; p < pend; ++p) {
-                    const uint32_t sy = lds_u8<0>(p);
-                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
-                    code = code * nsym + sy;
-                    if (run >= uk) {
-                        uint32_t col;
-                        if (MAP == 0) col = code;
-                        else if (MAP == 1) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(col) : "r"(col_addr + 2u * code));
-                        else { const int32_t c = __ldg(col_of_code + code); col = c >= 0 ? uint32_t(c) : uint32_t(K); }
-                        cnt_ops<OutT>::add(cnt_addr, col);
+            if (WORDS) {                                    // the rest of the last word is not part of this segment
+                if (lane < ((4 - (hi_i & 3)) & 3)) s_sym[hi_i + lane] = uint8_t(SYM_BAD);
+            }
+            if (first || WORDS) __syncwarp();
+            if (WORDS) {
+                // lane owns the C/4 words from word index w0; C = 4 * odd >= ceil(n / 32) symbols: conflict-free LDS.32
+                const int A = lo_i & ~3;
+                const int n = hi_i - A;
+                const int cw = (((n + 31) >> 5) + 3) >> 2 | 1;                    // words per lane (odd)
+                const int w0 = (A >> 2) + lane * cw, w1 = min(w0 + cw, (hi_i + 3) >> 2);
+                if (w0 < w1) {
+                    uint32_t pa = sym_addr + 4u * uint32_t(w0);
+                    uint32_t prev;
+                    asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(prev) : "r"(pa));
+                    uint32_t code = 0;
+                    for (uint32_t t = 0; t < km1; ++t) code = code * nsym + ((prev >> (out_shift + 8u * t)) & 0xFFu);
+                    const uint32_t npow = 0u - pow_k1;
+                    for (int w = w0; w < w1; ++w, pa += 4u) {
+                        uint32_t cur;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(pa));
+                        const uint32_t outw = __funnelshift_rc(prev, cur, out_shift);
+                        if ((((prev & prev_mask) | cur) & 0xC0C0C0C0u) == 0u) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                code = code * nsym + __byte_perm(cur, 0u, 0x4440u + j);
+                                cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
+                                code = __byte_perm(outw, 0u, 0x4440u + j) * npow + code;
+                            }
+                        } else {
+                            // bit i of inv: byte i of (previous : current) is not a symbol
+                            uint32_t inv = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                inv |= (((prev >> (8 * i)) & 0xC0u) ? 1u : 0u) << i;
+                                inv |= (((cur >> (8 * i)) & 0xC0u) ? 1u : 0u) << (4 + i);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                code = code * nsym + __byte_perm(cur, 0u, 0x4440u + j);
+                                if ((inv & (win_bits << (4u + j - km1))) == 0u) cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
+                                code = __byte_perm(outw, 0u, 0x4440u + j) * npow + code;
+                            }
+                        }
+                        prev = cur;
                     }
-                    code -= lds_u8<0>(p - back) * pow_k1;
+                }
+            } else {
+                // scan: lane owns symbols [i0, i1), warms up on the k-1 symbols in front of them
+                const int n = hi_i - lo_i;
+                const int C = ((((n + 31) >> 5) + 3) >> 2 | 1) << 2;     // smallest 4 * odd >= ceil(n / 32)
+                const int i0 = lo_i + lane * C, i1 = min(i0 + C, hi_i);
+                if (i0 < i1) {
+                    uint32_t run = 0, code = 0;
+                    uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
+                    for (uint32_t j = 1; j < uk; ++j, ++p) {
+                        const uint32_t sy = lds_u8<0>(p);
+                        run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                        code = code * nsym + sy;
+                    }
+                    const uint32_t pend = sym_addr + uint32_t(i1);
+                    const uint32_t back = uk - 1u;
+#pragma unroll 4
+                    for (; p < pend; ++p) {
+                        const uint32_t sy = lds_u8<0>(p);
+                        run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                        code = code * nsym + sy;
+                        if (run >= uk) cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
+                        code -= lds_u8<0>(p - back) * pow_k1;
+                    }
                 }
             }
             __syncwarp();
@@ -365,9 +428,11 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         if (per_sm_w < 1) per_sm_w = 1;
         const int grid_w = (int)std::min<int64_t>((nseq + CW_WARPS - 1) / CW_WARPS, int64_t(sm_count()) * per_sm_w);
         const int bulk_ok = ((size_t(K) * out_bytes) % 16 == 0) ? 1 : 0;
+        const char *force_bytes = getenv("SKM_CDW_BYTES");                      // A/B switch: the byte-wise scan of round 1
+        const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
 #define SKM_LAUNCH_DENSE_W(OUT, MAP)                                                                                 \
     {                                                                                                                \
-        auto kern = count_dense_warp_kernel<OUT, MAP>;                                                               \
+        auto kern = words ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>;      \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));          \
         kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
                                                     d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok,    \

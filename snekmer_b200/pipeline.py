@@ -111,14 +111,14 @@ class HostVectors:
         return self.counts() > 0
 
 
-def _upload_chunks(residues: torch.Tensor, offsets: np.ndarray, chunks, dev, s_in, main, on_chunk):
-    """Residues -> HBM chunk by chunk on the copy stream; on_chunk(batch) is called (on the main stream, after the
-    chunk has landed) for each.  Returns the chunk batches."""
+def _enqueue_uploads(residues: torch.Tensor, offsets: np.ndarray, chunks, dev, s_in, main):
+    """Residues -> HBM chunk by chunk on the copy stream, ALL enqueued up front.  Returns (batches, events): batch i may
+    be used on a stream that has waited for event i."""
     nres = int(offsets[-1])
     d_res = torch.empty(max(nres, 1) + 16, dtype=torch.uint8, device=dev)
     d_off = torch.from_numpy(offsets).to(dev, non_blocking=True)
     s_in.wait_stream(main)
-    batches = []
+    batches, events = [], []
     for lo, hi in chunks:
         r0, r1 = int(offsets[lo]), int(offsets[hi])
         with torch.cuda.stream(s_in):
@@ -126,13 +126,11 @@ def _upload_chunks(residues: torch.Tensor, offsets: np.ndarray, chunks, dev, s_i
                 d_res[r0:r1].copy_(residues[r0:r1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(s_in)
-        main.wait_event(ev)
         b = E.SequenceBatch(d_res, d_off[lo:hi + 1], offsets[lo:hi + 1])
         b.nres = r1                      # kernels may read the buffer up to the end of this chunk
         batches.append(b)
-        if on_chunk is not None:
-            on_chunk(b)
-    return batches
+        events.append(ev)
+    return batches, events
 
 
 def vectorize_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int, min_filter: int = 0,
@@ -156,16 +154,25 @@ def vectorize_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     chunks = _chunks_by_residues(offsets, n_chunks)
     order_only = min_filter <= 0 and E.order_only_supported(S)
-    if order_only:                      # the basis order needs first positions only: the walk ends once the space is saturated
+    batches, up_events = _enqueue_uploads(residues, offsets, chunks, dev, s_in, main)
+    if order_only:
+        # The basis order needs first positions only, and they are final once every code of the space has one.  The walk
+        # follows the upload chunk by chunk and the 4-byte "saturated" flag is read back after each chunk: as soon as
+        # it is set the basis is finalised and the count pass starts on the chunks already in HBM while the rest of the
+        # upload is still in flight (PCIe is full duplex: the upload then hides behind the download).
         first = torch.full((S,), -1, dtype=torch.int64, device=dev)
         state = torch.zeros(4, dtype=torch.int32, device=dev)
-        batches = _upload_chunks(residues, offsets, chunks, dev, s_in, main,
-                                 lambda b: E.basis_first_progressive(b, alphabet, k, first, state, 0))
+        for b, ev in zip(batches, up_events):
+            main.wait_event(ev)
+            E.basis_first_progressive(b, alphabet, k, first, state, 0)
+            if int(state[0].item()):
+                break
         basis = E.basis_finalize(alphabet, k, None, first, 0)           # reads K back (one 8-byte sync)
     else:
         count, first = E.basis_tables(S, dev)
-        batches = _upload_chunks(residues, offsets, chunks, dev, s_in, main,
-                                 lambda b: E.basis_accumulate(b, alphabet, k, count, first, 0))
+        for b, ev in zip(batches, up_events):
+            main.wait_event(ev)
+            E.basis_accumulate(b, alphabet, k, count, first, 0)
         basis = E.basis_finalize(alphabet, k, count, first, min_filter)
     K = basis.K
     host_dtype = {"int32": torch.int32, "uint16": torch.uint16, "uint8": torch.uint8, "bits": torch.uint8}[transport]
@@ -185,6 +192,7 @@ def vectorize_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int
     free_ev = [None, None]
     for i, ((lo, hi), b) in enumerate(zip(chunks, batches)):
         slot = i & 1
+        main.wait_event(up_events[i])
         if free_ev[slot] is not None:
             main.wait_event(free_ev[slot])
         cbuf = bufs[0 if packed else slot][: hi - lo]
@@ -241,7 +249,7 @@ class HostScores:
 
 
 def apply_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int, prepared: E.PreparedAnnotations,
-               basis: Optional[E.Basis] = None, n_chunks: int = 8, device=None,
+               basis: Optional[E.Basis] = None, n_chunks: int = 4, device=None,
                out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> HostScores:
     """Host query residues -> host top-2 annotations and cosine scores against a prepared annotation matrix
     (apply.smk:188-206 counts + :278-335 scoring).  Chunks of queries are uploaded on a copy stream while the previous
@@ -256,11 +264,12 @@ def apply_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int, pr
     if out is None:
         out = (torch.empty(n, dtype=torch.int32, pin_memory=True), torch.empty(n, dtype=torch.int32, pin_memory=True),
                torch.empty(n, dtype=torch.float64, pin_memory=True), torch.empty(n, dtype=torch.float64, pin_memory=True))
-    batches = _upload_chunks(residues, offsets, chunks, dev, s_in, main, None)
+    batches, up_events = _enqueue_uploads(residues, offsets, chunks, dev, s_in, main)
     rows_max = max(hi - lo for lo, hi in chunks) if chunks else 0
     K = prepared.K
     Qbuf = torch.empty((rows_max, K), dtype=torch.int32, device=dev)
-    for (lo, hi), b in zip(chunks, batches):
+    for (lo, hi), b, ev in zip(chunks, batches, up_events):
+        main.wait_event(ev)
         Q = E.count_dense(b, alphabet, k, basis, out=Qbuf[: hi - lo])
         r = E.apply_tc(Q, prepared, E.row_norm2(Q))
         if r is None:

@@ -206,7 +206,7 @@ def test_apply_counts_sparse_query_kmerlist_restriction():
     from snekmer_b200 import rules_sparse as RS
 
     rng = np.random.default_rng(9)
-    a, k = 2, 4
+    a, k = 2, 6
     ids = [f"tr|T{i:04d}|x" for i in range(400)]
     seqs = _rand_seqs(rng, 400, 20, 200, p_x=0.0)
     ann = {f"T{i:04d}": f"FAM{int(rng.integers(0, 9))}" for i in range(400) if rng.random() < 0.8}
@@ -217,7 +217,7 @@ def test_apply_counts_sparse_query_kmerlist_restriction():
     q_seqs = _rand_seqs(rng, 150, 10, 200, p_x=0.0)
     q_red = [O.reduce_str(s, a) for s in q_seqs]
     qb = E.SequenceBatch.from_strings(q_seqs)
-    q_basis = E.build_basis(qb, a, k, 3)                                    # min_filter = 3 drops rare k-mers
+    q_basis = E.build_basis(qb, a, k, 12)                                   # min_filter = 12 drops the rarer k-mers
     q_kmers = list(q_basis.kmers())
     assert 0 < len(q_kmers) < len(syms) ** k
     all_kmers = list(E.decode_kmers(np.arange(len(syms) ** k, dtype=np.uint64), syms, k))
