@@ -154,13 +154,6 @@ constexpr int CW_SYM = ts_sym_bytes(CW_SEG);      // 480
 // symbols are used raw (an invalid symbol's garbage digit is added and later subtracted with the same value, and no
 // window containing it is ever emitted), and the column comes from shared memory: 13 SASS instructions per residue
 // against 24 for the generic scanner.
-// WORDS (k - 1 <= 4, i.e. every dense basis of practical size): the scan reads its symbols as aligned 32-bit words —
-// a lane owns a 4-aligned chunk, keeps the previous word in a register and gets the four symbols that LEAVE the
-// window from one funnel shift of (previous : current) — instead of two LDS.U8 per residue, and it needs no run
-// counter: a word whose 4 symbols and the k-1 symbols in front of it are all valid (99.4 % of them) emits its four
-// windows unconditionally; the others (sequence start, X / B / Z ...) test each window against the invalid-byte mask
-// of the (previous : current) pair.  Measured on C2: 700 -> ~490 warp instructions and 221 -> ~190 shared wavefronts
-// per sequence (profiles/R2*).
 template <typename OutT, int MAP>
 __device__ __forceinline__ void cw_emit(uint32_t code, uint32_t cnt_addr, uint32_t col_addr, const int32_t *__restrict__ col_of_code, int K) {
     uint32_t col;
@@ -170,12 +163,29 @@ __device__ __forceinline__ void cw_emit(uint32_t code, uint32_t cnt_addr, uint32
     cnt_ops<OutT>::add(cnt_addr, col);
 }
 
-template <typename OutT, int MAP, bool WORDS>
+// Branch-free emission: an invalid window is counted into the dummy counter behind the row (MAP 0: column K; MAP 1:
+// the extra map entry S points at it), so the compiler can issue LDS.U16 + ATOMS without a branch around them.
+template <typename OutT, int MAP>
+__device__ __forceinline__ void cw_emit_sel(uint32_t code, bool ok, uint32_t cnt_addr, uint32_t col_addr,
+                                            const int32_t *__restrict__ col_of_code, int S, int K) {
+    if (MAP == 2) {
+        if (ok) cw_emit<OutT, 2>(code, cnt_addr, col_addr, col_of_code, K);
+        return;
+    }
+    uint32_t col;
+    if (MAP == 0) col = ok ? code : uint32_t(K);
+    else asm volatile("ld.shared.u16 %0, [%1];" : "=r"(col) : "r"(col_addr + 2u * (ok ? code : uint32_t(S))));
+    cnt_ops<OutT>::add(cnt_addr, col);
+}
+
+// First version of the warp kernel (round 1): translated symbols staged as bytes, two LDS.U8 per residue, a run
+// counter.  Still the path for k - 1 > 4 (and the A/B reference: SKM_CDW_BYTES=1).
+template <typename OutT, int MAP>
 __global__ void __launch_bounds__(32 * CW_WARPS, 6)
-count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
-                        const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
-                        const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
-                        OutT *__restrict__ out) {
+count_dense_warp_bytes_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
+                              const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
+                              const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
+                              OutT *__restrict__ out) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ uint8_t s_lut[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,12 +214,6 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
     lo = __shfl_sync(FULL, lo, 0);
     hi = __shfl_sync(FULL, hi, 0);
     const uint32_t uk = uint32_t(k);
-    const uint32_t km1 = uk - 1u;
-    // WORDS: shift that turns (previous : current) into the word of outgoing symbols, mask of the k-1 bytes of the
-    // previous word a window of this word can reach into, and the k-bit window mask over the pair's 8 validity bits
-    const uint32_t out_shift = 32u - 8u * km1;
-    const uint32_t prev_mask = km1 ? (0xC0C0C0C0u << (out_shift & 31u)) : 0u;
-    const uint32_t win_bits = (1u << uk) - 1u;
     int64_t e = (lo < hi) ? __ldg(off + lo) : 0;
     for (int64_t s = lo; s < hi; ++s) {
         const int64_t b = e;
@@ -246,76 +250,29 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
             __syncwarp();
             if (first) {                                    // nothing in front of the sequence start is a residue of it
                 for (int i = lane; i < lo_i; i += 32) s_sym[i] = uint8_t(SYM_BAD);
+                __syncwarp();
             }
-            if (WORDS) {                                    // the rest of the last word is not part of this segment
-                if (lane < ((4 - (hi_i & 3)) & 3)) s_sym[hi_i + lane] = uint8_t(SYM_BAD);
-            }
-            if (first || WORDS) __syncwarp();
-            if (WORDS) {
-                // lane owns the C/4 words from word index w0; C = 4 * odd >= ceil(n / 32) symbols: conflict-free LDS.32
-                const int A = lo_i & ~3;
-                const int n = hi_i - A;
-                const int cw = (((n + 31) >> 5) + 3) >> 2 | 1;                    // words per lane (odd)
-                const int w0 = (A >> 2) + lane * cw, w1 = min(w0 + cw, (hi_i + 3) >> 2);
-                if (w0 < w1) {
-                    uint32_t pa = sym_addr + 4u * uint32_t(w0);
-                    uint32_t prev;
-                    asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(prev) : "r"(pa));
-                    uint32_t code = 0;
-                    for (uint32_t t = 0; t < km1; ++t) code = code * nsym + ((prev >> (out_shift + 8u * t)) & 0xFFu);
-                    const uint32_t npow = 0u - pow_k1;
-                    for (int w = w0; w < w1; ++w, pa += 4u) {
-                        uint32_t cur;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(pa));
-                        const uint32_t outw = __funnelshift_rc(prev, cur, out_shift);
-                        if ((((prev & prev_mask) | cur) & 0xC0C0C0C0u) == 0u) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                code = code * nsym + __byte_perm(cur, 0u, 0x4440u + j);
-                                cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
-                                code = __byte_perm(outw, 0u, 0x4440u + j) * npow + code;
-                            }
-                        } else {
-                            // bit i of inv: byte i of (previous : current) is not a symbol
-                            uint32_t inv = 0;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                inv |= (((prev >> (8 * i)) & 0xC0u) ? 1u : 0u) << i;
-                                inv |= (((cur >> (8 * i)) & 0xC0u) ? 1u : 0u) << (4 + i);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                code = code * nsym + __byte_perm(cur, 0u, 0x4440u + j);
-                                if ((inv & (win_bits << (4u + j - km1))) == 0u) cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
-                                code = __byte_perm(outw, 0u, 0x4440u + j) * npow + code;
-                            }
-                        }
-                        prev = cur;
-                    }
+            // scan: lane owns symbols [i0, i1), warms up on the k-1 symbols in front of them
+            const int n = hi_i - lo_i;
+            const int C = ((((n + 31) >> 5) + 3) >> 2 | 1) << 2;     // smallest 4 * odd >= ceil(n / 32)
+            const int i0 = lo_i + lane * C, i1 = min(i0 + C, hi_i);
+            if (i0 < i1) {
+                uint32_t run = 0, code = 0;
+                uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
+                for (uint32_t j = 1; j < uk; ++j, ++p) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + sy;
                 }
-            } else {
-                // scan: lane owns symbols [i0, i1), warms up on the k-1 symbols in front of them
-                const int n = hi_i - lo_i;
-                const int C = ((((n + 31) >> 5) + 3) >> 2 | 1) << 2;     // smallest 4 * odd >= ceil(n / 32)
-                const int i0 = lo_i + lane * C, i1 = min(i0 + C, hi_i);
-                if (i0 < i1) {
-                    uint32_t run = 0, code = 0;
-                    uint32_t p = sym_addr + uint32_t(i0) - (uk - 1u);
-                    for (uint32_t j = 1; j < uk; ++j, ++p) {
-                        const uint32_t sy = lds_u8<0>(p);
-                        run = (sy >= SYM_BAD) ? 0u : run + 1u;
-                        code = code * nsym + sy;
-                    }
-                    const uint32_t pend = sym_addr + uint32_t(i1);
-                    const uint32_t back = uk - 1u;
+                const uint32_t pend = sym_addr + uint32_t(i1);
+                const uint32_t back = uk - 1u;
 #pragma unroll 4
-                    for (; p < pend; ++p) {
-                        const uint32_t sy = lds_u8<0>(p);
-                        run = (sy >= SYM_BAD) ? 0u : run + 1u;
-                        code = code * nsym + sy;
-                        if (run >= uk) cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
-                        code -= lds_u8<0>(p - back) * pow_k1;
-                    }
+                for (; p < pend; ++p) {
+                    const uint32_t sy = lds_u8<0>(p);
+                    run = (sy >= SYM_BAD) ? 0u : run + 1u;
+                    code = code * nsym + sy;
+                    if (run >= uk) cw_emit<OutT, MAP>(code, cnt_addr, col_addr, col_of_code, K);
+                    code -= lds_u8<0>(p - back) * pow_k1;
                 }
             }
             __syncwarp();
@@ -340,6 +297,167 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
         }
         for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
+    }
+}
+
+// Round-2 warp kernel (k - 1 <= 4, i.e. every dense basis of practical size).  What changed against the first version
+// (profiles/r1m_* -> R2b_* -> R2c_*): 700 warp instructions and 221 shared-memory wavefronts per sequence, 59 % of the
+// instructions OUTSIDE the scan loop (staging the translated symbols: 96; 64-bit position arithmetic per sequence and
+// segment: ~170).
+//   * the RAW residue bytes are staged (one LDG.128 + STS.128 per lane) and translated inside the scan, one LDS.U8 from
+//     the LUT per residue, straight into the register that feeds the rolling code: no translate-and-repack pass;
+//   * a lane owns a 4-ALIGNED chunk and reads it as 32-bit words; the translated previous word stays in a register and
+//     one funnel shift of (previous : current) gives the four symbols that leave the window: no second read per residue;
+//   * no run counter and no branch: the 8 validity bits of (previous : current) are tested against a k-bit window mask
+//     and the emission is predicated (a branch on "any invalid byte" diverges in 54 % of the warp iterations — first
+//     word, last word, an X somewhere in 192 bytes — and made the first word-based version execute MORE instructions);
+//   * positions are 32-bit offsets from the warp's own (16-byte aligned) base, and the offsets of 31 sequences are
+//     fetched with one coalesced load and handed out by shuffles.
+template <typename OutT, int MAP>
+__global__ void __launch_bounds__(32 * CW_WARPS, 6)
+count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
+                        const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
+                        const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
+                        OutT *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t s_raw[];
+    __shared__ __align__(16) uint8_t s_lut[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint16_t *s_col = reinterpret_cast<uint16_t *>(s_raw);                       // [S] when MAP == 1
+    uint8_t *mine = s_raw + map_bytes + size_t(warp) * (row_bytes + CW_SYM);
+    uint4 *s_cnt4 = reinterpret_cast<uint4 *>(mine);
+    uint8_t *s_res = mine + row_bytes;                                           // raw residue bytes of the segment
+    uint32_t cnt_addr = smem_addr(mine), raw_addr = smem_addr(s_res), col_addr = smem_addr(s_col), lut_addr = smem_addr(s_lut);
+    asm volatile("" : "+r"(cnt_addr), "+r"(raw_addr), "+r"(col_addr), "+r"(lut_addr));
+    ts_lut_init(s_lut, lut);                                                     // invalid bytes -> SYM_BAD (0x40)
+    if (threadIdx.x == 0) s_lut[0] = uint8_t(SYM_BAD);                           // byte 0 pads the staged segment: never a symbol
+    if (MAP == 1)
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            const int32_t c = __ldg(col_of_code + i);
+            s_col[i] = uint16_t(c >= 0 ? c : K);                                // K = the dummy counter
+        }
+    if (MAP == 1 && threadIdx.x == 0) s_col[S] = uint16_t(K);                   // entry S: where invalid windows go
+    for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                                        // LUT and column map; the only CTA-wide barrier
+    // this warp's sequences: those that start in the w-th 1/W of the residue buffer
+    int64_t lo = 0, hi = 0;
+    if (lane == 0) {
+        const int64_t W = int64_t(gridDim.x) * CW_WARPS, w = int64_t(blockIdx.x) * CW_WARPS + warp;
+        const int64_t r0 = __ldg(off), span = __ldg(off + nseq) - r0;
+        lo = (w == 0) ? 0 : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * w) / W));
+        hi = (w + 1 == W) ? nseq : lower_bound_off(off, nseq, r0 + (int64_t)(((__int128)span * (w + 1)) / W));
+    }
+    lo = __shfl_sync(FULL, lo, 0);
+    hi = __shfl_sync(FULL, hi, 0);
+    if (lo >= hi) return;
+    // 32-bit positions relative to the 16-byte aligned base of this warp's range (alignment of a position is preserved)
+    const int64_t r_base = __ldg(off + lo) & ~int64_t(15);
+    const uint8_t *__restrict__ resw = res + r_base;
+    const int64_t lim64 = nres - r_base;                    // bytes that may be read from resw
+    const uint32_t lim = lim64 > int64_t(0xFFFFFFF0u) ? 0xFFFFFFF0u : uint32_t(lim64);
+    const uint32_t uk = uint32_t(k), km1 = uk - 1u;
+    const uint32_t out_shift = 32u - 8u * km1;              // (previous : current) >> out_shift = the four outgoing symbols
+    const uint32_t win0 = ((1u << uk) - 1u) << (4u - km1);  // validity bits a window ending at byte 0 of `current` covers
+    const uint32_t npow = 0u - pow_k1;
+    uint32_t tailw = 0;
+    for (int64_t s0 = lo; s0 < hi; s0 += 31) {
+        // one coalesced load of 32 offsets: sequences s0 .. s0+30 (b = rel[i], e = rel[i+1])
+        const int64_t si = min(s0 + lane, hi);
+        const uint32_t rel = uint32_t(__ldg(off + si) - r_base);
+        const int ns = (hi - s0 < 31) ? int(hi - s0) : 31;
+        for (int i = 0; i < ns; ++i) {
+            const uint32_t b = __shfl_sync(FULL, rel, i), e = __shfl_sync(FULL, rel, i + 1);
+            bool first = true;
+            for (uint32_t a = b; a < e;) {
+                const uint32_t a2 = min(e, (a + uint32_t(CW_SEG)) & ~15u);
+                const uint32_t base = a & ~15u;
+                const int lo_i = TS_PAD + int(a - base), hi_i = lo_i + int(a2 - a);
+                const int nvec = int((a2 - base + 15u) >> 4);
+                // stage the raw bytes [base, a2) at s_res[TS_PAD ...): one 16-byte vector per lane (at most 25)
+                if (lane < nvec) {
+                    const uint32_t p = base + 16u * uint32_t(lane);
+                    uint4 x;
+                    if (p + 16u <= lim) {
+                        x = __ldg(reinterpret_cast<const uint4 *>(resw + p));
+                    } else {
+                        uint32_t w4[4] = {0, 0, 0, 0};
+                        for (int j = 0; j < 16; ++j)
+                            if (p + uint32_t(j) < lim) w4[j >> 2] |= uint32_t(resw[p + j]) << (8 * (j & 3));
+                        x = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                    reinterpret_cast<uint4 *>(s_res + TS_PAD)[lane] = x;
+                }
+                if (!first && lane == 0) reinterpret_cast<uint32_t *>(s_res)[TS_PAD / 4 - 1] = tailw;   // the 4 bytes in front of this segment
+                __syncwarp();
+                // byte 0 translates to SYM_BAD: everything in front of the sequence and behind the segment's last word is invalid
+                if (first) for (int j = lane; j < lo_i; j += 32) s_res[j] = 0;
+                if (lane < ((4 - (hi_i & 3)) & 3)) s_res[hi_i + lane] = 0;
+                __syncwarp();
+                // lane owns cw words (cw odd -> conflict-free LDS.32) from word index w0
+                const int A = lo_i & ~3;
+                const int n = hi_i - A;
+                const int cw = (((n + 31) >> 5) + 3) >> 2 | 1;
+                const int w0 = (A >> 2) + lane * cw, w1 = min(w0 + cw, (hi_i + 3) >> 2);
+                if (w0 < w1) {
+                    uint32_t pa = raw_addr + 4u * uint32_t(w0);
+                    uint32_t raw;
+                    asm volatile("ld.shared.u32 %0, [%1+-4];" : "=r"(raw) : "r"(pa));
+                    uint32_t t0, t1, t2, t3;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4440u)));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4441u)));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t2) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4442u)));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t3) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4443u)));
+                    uint32_t prevT = t0 | (t1 << 8) | (t2 << 16) | (t3 << 24);
+                    uint32_t pinv = (((prevT >> 6) & 0x01010101u) * 0x01020408u) >> 24;      // bit i: byte i of prevT is no symbol
+                    uint32_t code = 0;
+                    for (uint32_t t = 0; t < km1; ++t) code = code * nsym + ((prevT >> (out_shift + 8u * t)) & 0xFFu);
+                    for (int w = w0; w < w1; ++w, pa += 4u) {
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(pa));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4440u)));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4441u)));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t2) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4442u)));
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t3) : "r"(lut_addr + __byte_perm(raw, 0u, 0x4443u)));
+                        const uint32_t curT = t0 | (t1 << 8) | (t2 << 16) | (t3 << 24);
+                        const uint32_t outw = __funnelshift_rc(prevT, curT, out_shift);
+                        const uint32_t cinv = (((curT >> 6) & 0x01010101u) * 0x01020408u) >> 24;
+                        const uint32_t inv8 = pinv | (cinv << 4);
+                        code = code * nsym + t0;
+                        cw_emit_sel<OutT, MAP>(code, (inv8 & win0) == 0u, cnt_addr, col_addr, col_of_code, S, K);
+                        code = __byte_perm(outw, 0u, 0x4440u) * npow + code;
+                        code = code * nsym + t1;
+                        cw_emit_sel<OutT, MAP>(code, (inv8 & (win0 << 1)) == 0u, cnt_addr, col_addr, col_of_code, S, K);
+                        code = __byte_perm(outw, 0u, 0x4441u) * npow + code;
+                        code = code * nsym + t2;
+                        cw_emit_sel<OutT, MAP>(code, (inv8 & (win0 << 2)) == 0u, cnt_addr, col_addr, col_of_code, S, K);
+                        code = __byte_perm(outw, 0u, 0x4442u) * npow + code;
+                        code = code * nsym + t3;
+                        cw_emit_sel<OutT, MAP>(code, (inv8 & (win0 << 3)) == 0u, cnt_addr, col_addr, col_of_code, S, K);
+                        code = __byte_perm(outw, 0u, 0x4443u) * npow + code;
+                        prevT = curT;
+                        pinv = cinv;
+                    }
+                }
+                __syncwarp();
+                if (a2 < e && lane == 0) tailw = reinterpret_cast<const uint32_t *>(s_res)[(hi_i >> 2) - 1];   // hi_i is 16-aligned here
+                __syncwarp();
+                first = false;
+                a = a2;
+            }
+            // ---- flush: the row is one contiguous K * sizeof(OutT) range of the output ----
+            OutT *dst = out + (s0 + i) * K;
+            if (bulk_ok) {
+                ts_bulk_fence();
+                __syncwarp();
+                if (lane == 0) { ts_bulk_store(dst, cnt_addr, uint32_t(K) * uint32_t(sizeof(OutT))); ts_bulk_wait_read(); }
+                __syncwarp();
+            } else {
+                __syncwarp();
+                const OutT *s_cnt = reinterpret_cast<const OutT *>(mine);
+                for (int j = lane; j < K; j += 32) dst[j] = s_cnt[j];
+                __syncwarp();
+            }
+            for (int j = lane; j < int(row_bytes >> 4); j += 32) s_cnt4[j] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+        }
     }
 }
 
@@ -421,7 +539,7 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
     const char *force_tile = getenv("SKM_CD_TILE");
     if (row_bytes + CW_SYM <= 9 * 1024 + 256 && K < 65535 && !(force_tile && atoi(force_tile))) {
         const int map_mode = !d_col_of_code ? 0 : (S <= 16384 ? 1 : 2);
-        const uint32_t map_bytes = map_mode == 1 ? uint32_t((size_t(S) * 2 + 127) & ~size_t(127)) : 0u;
+        const uint32_t map_bytes = map_mode == 1 ? uint32_t((size_t(S + 1) * 2 + 127) & ~size_t(127)) : 0u;     // + the entry for invalid windows
         const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM);
         int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 256));
         if (per_sm_w > 6) per_sm_w = 6;
@@ -432,7 +550,7 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
 #define SKM_LAUNCH_DENSE_W(OUT, MAP)                                                                                 \
     {                                                                                                                \
-        auto kern = words ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>;      \
+        auto kern = words ? count_dense_warp_kernel<OUT, MAP> : count_dense_warp_bytes_kernel<OUT, MAP>;             \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));          \
         kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
                                                     d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok,    \
