@@ -312,8 +312,12 @@ count_dense_warp_bytes_kernel(const uint8_t *__restrict__ res, int64_t nres, con
 //     and the emission is predicated (a branch on "any invalid byte" diverges in 54 % of the warp iterations — first
 //     word, last word, an X somewhere in 192 bytes — and made the first word-based version execute MORE instructions);
 //   * positions are 32-bit offsets from the warp's own (16-byte aligned) base, and the offsets of 31 sequences are
-//     fetched with one coalesced load and handed out by shuffles.
-template <typename OutT, int MAP>
+//     fetched with one coalesced load and handed out by shuffles;
+//   * a flushed row is re-zeroed by the copy engine (cp.async.bulk shared -> shared from a zero row of the CTA,
+//     completing on the warp's mbarrier while the next sequence is being staged) instead of 8 STS.128 per lane: the
+//     kernel is bound by the LSU wavefront pipe (85 % busy, the SRAM banks themselves 14 %), and zeroing was 32 of its
+//     189 wavefronts per sequence.  (ZFILL = 0 keeps the stores: rows that do not fit a second copy per CTA.)
+template <typename OutT, int MAP, bool ZFILL>
 __global__ void __launch_bounds__(32 * CW_WARPS, 6)
 count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
                         const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
@@ -321,9 +325,12 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
                         OutT *__restrict__ out) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(16) uint8_t s_lut[256];
+    __shared__ __align__(8) uint64_t s_bar[CW_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint16_t *s_col = reinterpret_cast<uint16_t *>(s_raw);                       // [S] when MAP == 1
     uint8_t *mine = s_raw + map_bytes + size_t(warp) * (row_bytes + CW_SYM);
+    uint4 *s_zero4 = reinterpret_cast<uint4 *>(s_raw + map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM));   // ZFILL: row_bytes of zeros
+    const uint32_t bar = smem_addr(&s_bar[warp]), zero_addr = smem_addr(s_zero4);
     uint4 *s_cnt4 = reinterpret_cast<uint4 *>(mine);
     uint8_t *s_res = mine + row_bytes;                                           // raw residue bytes of the segment
     uint32_t cnt_addr = smem_addr(mine), raw_addr = smem_addr(s_res), col_addr = smem_addr(s_col), lut_addr = smem_addr(s_lut);
@@ -337,7 +344,14 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
         }
     if (MAP == 1 && threadIdx.x == 0) s_col[S] = uint16_t(K);                   // entry S: where invalid windows go
     for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();                                        // LUT and column map; the only CTA-wide barrier
+    if (ZFILL) {
+        for (int i = threadIdx.x; i < int(row_bytes >> 4); i += blockDim.x) s_zero4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) ts_mbar_init(bar, 1);
+        ts_bulk_fence();                                    // the zero row is read by the async proxy
+    }
+    __syncthreads();                                        // LUT, column map, zero row; the only CTA-wide barrier
+    uint32_t zphase = 0;
+    bool zpending = false;                                  // a zero-fill of this warp's row is in flight
     // this warp's sequences: those that start in the w-th 1/W of the residue buffer
     int64_t lo = 0, hi = 0;
     if (lane == 0) {
@@ -389,9 +403,10 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
                 if (!first && lane == 0) reinterpret_cast<uint32_t *>(s_res)[TS_PAD / 4 - 1] = tailw;   // the 4 bytes in front of this segment
                 __syncwarp();
                 // byte 0 translates to SYM_BAD: everything in front of the sequence and behind the segment's last word is invalid
-                if (first) for (int j = lane; j < lo_i; j += 32) s_res[j] = 0;
+                if (first) { const int f0 = (lo_i & ~3) - 4; if (f0 + lane < lo_i) s_res[f0 + lane] = 0; }   // previous word + front of the first word
                 if (lane < ((4 - (hi_i & 3)) & 3)) s_res[hi_i + lane] = 0;
                 __syncwarp();
+                if (ZFILL && zpending) { ts_mbar_wait(bar, zphase); zphase ^= 1u; zpending = false; }   // the row is zero again
                 // lane owns cw words (cw odd -> conflict-free LDS.32) from word index w0
                 const int A = lo_i & ~3;
                 const int n = hi_i - A;
@@ -444,6 +459,7 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
             }
             // ---- flush: the row is one contiguous K * sizeof(OutT) range of the output ----
             OutT *dst = out + (s0 + i) * K;
+            if (ZFILL && zpending) { ts_mbar_wait(bar, zphase); zphase ^= 1u; zpending = false; }       // (a sequence without residues)
             if (bulk_ok) {
                 ts_bulk_fence();
                 __syncwarp();
@@ -455,7 +471,15 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
                 for (int j = lane; j < K; j += 32) dst[j] = s_cnt[j];
                 __syncwarp();
             }
-            for (int j = lane; j < int(row_bytes >> 4); j += 32) s_cnt4[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (ZFILL) {
+                if (s0 + i + 1 < hi) {                      // (nothing may be in flight into this CTA's memory when the warp exits)
+                    if (!bulk_ok) ts_bulk_fence();          // the plain-load flush above read the row through the generic proxy
+                    if (lane == 0) { ts_mbar_expect_tx(bar, row_bytes); ts_bulk_copy_s2s(cnt_addr, zero_addr, row_bytes, bar); }
+                    zpending = true;
+                }
+            } else {
+                for (int j = lane; j < int(row_bytes >> 4); j += 32) s_cnt4[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
             __syncwarp();
         }
     }
@@ -540,17 +564,20 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
     if (row_bytes + CW_SYM <= 9 * 1024 + 256 && K < 65535 && !(force_tile && atoi(force_tile))) {
         const int map_mode = !d_col_of_code ? 0 : (S <= 16384 ? 1 : 2);
         const uint32_t map_bytes = map_mode == 1 ? uint32_t((size_t(S + 1) * 2 + 127) & ~size_t(127)) : 0u;     // + the entry for invalid windows
-        const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM);
-        int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 256));
+        const char *force_bytes = getenv("SKM_CDW_BYTES");                      // A/B switch: the byte-wise scan of round 1
+        const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
+        const char *no_zfill = getenv("SKM_CDW_NOZFILL");                       // A/B switch: re-zero the row with stores
+        const bool zfill = words && !(no_zfill && atoi(no_zfill));
+        const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM) + (zfill ? row_bytes : 0);
+        int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 512));
         if (per_sm_w > 6) per_sm_w = 6;
         if (per_sm_w < 1) per_sm_w = 1;
         const int grid_w = (int)std::min<int64_t>((nseq + CW_WARPS - 1) / CW_WARPS, int64_t(sm_count()) * per_sm_w);
         const int bulk_ok = ((size_t(K) * out_bytes) % 16 == 0) ? 1 : 0;
-        const char *force_bytes = getenv("SKM_CDW_BYTES");                      // A/B switch: the byte-wise scan of round 1
-        const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
 #define SKM_LAUNCH_DENSE_W(OUT, MAP)                                                                                 \
     {                                                                                                                \
-        auto kern = words ? count_dense_warp_kernel<OUT, MAP> : count_dense_warp_bytes_kernel<OUT, MAP>;             \
+        auto kern = !words ? count_dense_warp_bytes_kernel<OUT, MAP>                                                 \
+                           : (zfill ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>);  \
         SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));          \
         kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
                                                     d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok,    \
