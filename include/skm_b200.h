@@ -377,6 +377,32 @@ SKM_API int skm_pack_presence_bits(const void *d_counts, int64_t rows, int64_t c
 SKM_API int skm_rows_out_of_range_i32(const int32_t *d_X, int64_t rows, int64_t cols, int32_t lo, int32_t hi,
                               int32_t *d_rows_out, int64_t capacity, int64_t *d_n_out, skm_stream_t stream);
 
+/* (a12) learn for the heavy annotations: dense count rows (learn.smk:306-326,385-408 when a few families own most of
+ * the sequences).  d_rows is uint32 [n_rows, S] (S = nsym^k <= 2^27), zeroed by the caller.
+ * skm_rows_accumulate: rows[row_of_seq[s]][code] += 1 for every valid window of sequence s; sequences with
+ *   row_of_seq < 0 are skipped.  Fast when the sequences of a row are adjacent (skm_gather_sequences): the row then
+ *   stays in L2.  Fewer than 2^32 residues per call.
+ * skm_rows_block_counts: d_counts int32 [n_rows, ceil(S / skm_rows_block())] = non-zeros per block of codes.
+ * skm_rows_emit: the non-zeros of block (r, b), in code order, as (ann_of_row[r] * S + code, count) from
+ *   d_keys_out[d_row_dst[r] + d_block_offsets[r * nblk + b]] on — the caller's exclusive prefix sums of the block
+ *   counts inside a row and the place of the row's annotation in the merged sorted list.
+ * skm_rows_colsum: d_totals[c] += sum over rows (the Totals row of learn.smk:380; not atomic: one launch at a time).
+ * skm_coo_shift_copy: out[i + shift(i)] = in[i] for a sorted COO list, shift(i) = d_insert_cum[h] for the largest h
+ *   with d_insert_pos[h] <= i (0 below d_insert_pos[0]): makes room for blocks inserted at list positions
+ *   d_insert_pos (ascending), d_insert_cum = inclusive prefix sums of the blocks' sizes. */
+SKM_API int skm_rows_accumulate(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                        const uint8_t *d_lut, int nsym, int k, const int32_t *d_row_of_seq, int64_t S,
+                        uint32_t *d_rows, skm_stream_t stream);
+SKM_API int skm_rows_block(void);
+SKM_API int skm_rows_block_counts(const uint32_t *d_rows, int64_t n_rows, int64_t S, int32_t *d_counts, skm_stream_t stream);
+SKM_API int skm_rows_emit(const uint32_t *d_rows, int64_t n_rows, int64_t S, const int64_t *d_block_offsets,
+                  const int64_t *d_row_dst, const int64_t *d_ann_of_row, uint64_t *d_keys_out, int64_t *d_vals_out,
+                  int64_t out_capacity, skm_stream_t stream);
+SKM_API int skm_rows_colsum(const uint32_t *d_rows, int64_t n_rows, int64_t S, int64_t *d_totals, skm_stream_t stream);
+SKM_API int skm_coo_shift_copy(const uint64_t *d_keys, const int64_t *d_vals, int64_t n, const int64_t *d_insert_pos,
+                       const int64_t *d_insert_cum, int64_t n_insert, uint64_t *d_keys_out, int64_t *d_vals_out,
+                       skm_stream_t stream);
+
 /* Measurement helper (not on the product path): a kernel of `blocks` x 256 threads, each running 16 independent
  * chains of `iters` fp32 FMAs; *flops_out (host) = the flops it executes.  Timed with CUDA events by
  * scripts/measure_peaks.py it gives the fp32-FMA peak the sparse scoring roofline is quoted against.

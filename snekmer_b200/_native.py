@@ -92,6 +92,12 @@ SIGNATURES = {
     "skm_pack_presence_bits": (_int, [_p, _i64, _i64, _int, _p, _p]),
     "skm_rows_out_of_range_i32": (_int, [_p, _i64, _i64, C.c_int32, C.c_int32, _p, _i64, _p, _p]),
     "skm_bench_fma_f32": (_int, [_i64, _int, _p, C.POINTER(C.c_double), _p]),
+    "skm_rows_accumulate": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _p, _p]),
+    "skm_rows_block": (_int, []),
+    "skm_rows_block_counts": (_int, [_p, _i64, _i64, _p, _p]),
+    "skm_rows_emit": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "skm_rows_colsum": (_int, [_p, _i64, _i64, _p, _p]),
+    "skm_coo_shift_copy": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p]),
     "skm_scatter_add_i64": (_int, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _p]),
 }
 

@@ -16,6 +16,7 @@
 // Sparse path (skm_count_csr): window codes -> columns, segmented radix sort of
 // each sequence's keys, run-length encode into CSR.
 #include <cstdlib>
+#include <cstring>
 
 #include <cub/cub.cuh>
 
@@ -146,6 +147,8 @@ constexpr int CW_WARPS = 8;
 constexpr int CW_C = 12;                          // residues per lane and segment (4 * odd: conflict-free byte reads)
 constexpr int CW_SEG = 32 * CW_C;
 constexpr int CW_SYM = ts_sym_bytes(CW_SEG);      // 480
+constexpr size_t CW_ZPOOL = 1u << 20;             // zero-initialised device memory: L2-resident source of the bulk zero-fill (A/B variant)
+__device__ __align__(128) uint8_t g_cw_zero[CW_ZPOOL];
 
 // MAP: 0 = identity basis (column = code), 1 = col_of_code staged in shared memory as uint16 columns (S <= 16384;
 // filtered codes point at a dummy counter behind the row, so the scan needs no validity test), 2 = col_of_code read
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(32 * CW_WARPS, 6)
 count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
                         const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
                         const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
-                        OutT *__restrict__ out) {
+                        OutT *__restrict__ out, const uint8_t *__restrict__ zsrc) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(16) uint8_t s_lut[256];
     __shared__ __align__(8) uint64_t s_bar[CW_WARPS];
@@ -474,7 +477,11 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
             if (ZFILL) {
                 if (s0 + i + 1 < hi) {                      // (nothing may be in flight into this CTA's memory when the warp exits)
                     if (!bulk_ok) ts_bulk_fence();          // the plain-load flush above read the row through the generic proxy
-                    if (lane == 0) { ts_mbar_expect_tx(bar, row_bytes); ts_bulk_copy_s2s(cnt_addr, zero_addr, row_bytes, bar); }
+                    if (lane == 0) {
+                        ts_mbar_expect_tx(bar, row_bytes);
+                        if (zsrc) ts_bulk_copy_g2s(cnt_addr, zsrc + ((size_t(blockIdx.x) * CW_WARPS + warp) * 4096u) % (CW_ZPOOL - 16384u), row_bytes, bar);
+                        else ts_bulk_copy_s2s(cnt_addr, zero_addr, row_bytes, bar);
+                    }
                     zpending = true;
                 }
             } else {
@@ -567,7 +574,15 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         const char *force_bytes = getenv("SKM_CDW_BYTES");                      // A/B switch: the byte-wise scan of round 1
         const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
         const char *no_zfill = getenv("SKM_CDW_NOZFILL");                       // A/B switch: re-zero the row with stores
-        const bool zfill = words && !(no_zfill && atoi(no_zfill));
+        const char *zmode = getenv("SKM_CDW_ZFILL");                            // smem (default) | smem_nocluster | l2 | off
+        const bool zfill = words && !(no_zfill && atoi(no_zfill)) && !(zmode && !strcmp(zmode, "off"));
+        const bool zfill_cluster = zfill && !(zmode && !strcmp(zmode, "smem_nocluster"));   // shared -> shared bulk copies address shared::cluster: launch as a cluster of one
+        const uint8_t *zsrc = nullptr;
+        if (zfill && zmode && !strcmp(zmode, "l2")) {
+            void *sym = nullptr;
+            SKM_CUDA_TRY(cudaGetSymbolAddress(&sym, g_cw_zero));
+            zsrc = (const uint8_t *)sym;
+        }
         const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM) + (zfill ? row_bytes : 0);
         int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 512));
         if (per_sm_w > 6) per_sm_w = 6;
@@ -576,12 +591,23 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         const int bulk_ok = ((size_t(K) * out_bytes) % 16 == 0) ? 1 : 0;
 #define SKM_LAUNCH_DENSE_W(OUT, MAP)                                                                                 \
     {                                                                                                                \
-        auto kern = !words ? count_dense_warp_bytes_kernel<OUT, MAP>                                                 \
-                           : (zfill ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>);  \
-        SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));          \
-        kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
-                                                    d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok,    \
-                                                    (OUT *)d_counts);                                                \
+        if (!words) {                                                                                                \
+            auto kern = count_dense_warp_bytes_kernel<OUT, MAP>;                                                     \
+            SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));      \
+            kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
+                                                        d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok, (OUT *)d_counts); \
+        } else {                                                                                                     \
+            auto kern = zfill ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>;  \
+            SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));      \
+            cudaLaunchConfig_t cfg = {};                                                                             \
+            cfg.gridDim = dim3((unsigned)grid_w); cfg.blockDim = dim3(32 * CW_WARPS); cfg.dynamicSmemBytes = smem_w; cfg.stream = st; \
+            cudaLaunchAttribute attr[1];                                                                             \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                                        \
+            attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                \
+            cfg.attrs = attr; cfg.numAttrs = zfill_cluster ? 1 : 0;                                                  \
+            SKM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
+                                            d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok, (OUT *)d_counts, zsrc)); \
+        }                                                                                                            \
     }
 #define SKM_LAUNCH_DENSE_WM(OUT)                                                                                     \
     { if (map_mode == 0) SKM_LAUNCH_DENSE_W(OUT, 0) else if (map_mode == 1) SKM_LAUNCH_DENSE_W(OUT, 1) else SKM_LAUNCH_DENSE_W(OUT, 2) }

@@ -312,6 +312,11 @@ __device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// global -> this CTA's shared memory (16-byte aligned, bytes % 16 == 0), completing on the mbarrier
+__device__ __forceinline__ void ts_bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // dst / src: shared::cta addresses of this CTA, 16-byte aligned, bytes % 16 == 0
 __device__ __forceinline__ void ts_bulk_copy_s2s(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -828,16 +828,131 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
     return coo_merge(torch.cat(parts_k), torch.cat(parts_v), key_bound=n_ann * S)
 
 
-def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int):
+HEAVY_ROW_DIV = 4                # an annotation is "heavy" when it has more residues than S / HEAVY_ROW_DIV ...
+HEAVY_ROWS_MAX_BYTES = 8 << 30   # ... as long as the dense rows of all heavy annotations stay below this
+
+
+def _learn_rows(batch: SequenceBatch, tab: AlphabetTables, k: int, ann_id: torch.Tensor, n_ann: int, S: int,
+                want_totals: bool, heavy_div: int):
+    """Dense-row part of learn_sparse_hybrid: returns (rows uint32 [R, S], heavy annotation ids int64 [H] ascending,
+    rest_row index or -1).  Rows 0..H-1 are the heavy annotations, row H (when want_totals) the unannotated sequences."""
+    dev = batch.device
+    lens = (batch.offsets[1:] - batch.offsets[:-1])
+    valid = (ann_id >= 0) & (ann_id < n_ann)
+    per_ann = torch.zeros(n_ann + 1, dtype=torch.int64, device=dev)
+    per_ann.index_add_(0, torch.where(valid, ann_id, torch.full_like(ann_id, n_ann)).to(torch.int64), lens)
+    thr = max(S // max(int(heavy_div), 1), 1)
+    heavy_mask = per_ann[:n_ann] > thr
+    max_rows = max(int(HEAVY_ROWS_MAX_BYTES // (4 * S)) - 1, 0)
+    heavy = torch.nonzero(heavy_mask).reshape(-1)
+    if heavy.numel() > max_rows:                         # keep the largest ones
+        order = torch.argsort(per_ann[heavy], descending=True)[:max_rows]
+        heavy = torch.sort(heavy[order]).values
+    H = int(heavy.numel())                               # one sync
+    rest_row = H if want_totals else -1
+    R = H + (1 if want_totals else 0)
+    if R == 0:
+        return None, heavy, -1
+    row_of_ann = torch.full((n_ann + 1,), -1, dtype=torch.int32, device=dev)
+    row_of_ann[heavy] = torch.arange(H, dtype=torch.int32, device=dev)
+    row_of_ann[n_ann] = rest_row
+    row_of_seq = row_of_ann[torch.where(valid, ann_id, torch.full_like(ann_id, n_ann)).to(torch.int64)].contiguous()
+    # the sequences of a row next to each other: the row stays in L2 while they stream past
+    sel = torch.nonzero(row_of_seq >= 0).reshape(-1)
+    order = torch.sort(row_of_seq[sel].to(torch.int64), stable=True).indices
+    sel = sel[order]
+    rows = torch.zeros((R, S), dtype=torch.int32, device=dev)
+    if sel.numel():
+        g_res, g_off = gather_sequences(batch, sel)
+        g_row = row_of_seq[sel].contiguous()
+        total = int(g_off[-1].item())
+        # < 2^32 residues per call: chunk by sequences when a shard is larger
+        bounds = [0, sel.numel()]
+        if total >= (1 << 32) - 64:
+            step = max(1, sel.numel() // (total // ((1 << 31)) + 1))
+            bounds = list(range(0, sel.numel(), step)) + [sel.numel()]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            e0, e1 = (int(x) for x in g_off[torch.tensor([lo, hi], device=dev)].tolist())
+            base = e0 & ~15
+            offs = (g_off[lo:hi + 1] - base).contiguous()
+            check(lib().skm_rows_accumulate(_ptr(g_res[base:]), e1 - base, _ptr(offs), hi - lo, _ptr(tab.lut), tab.nsym, int(k),
+                                            _ptr(g_row[lo:hi]), int(S), _ptr(rows), _stream()))
+    return rows, heavy, rest_row
+
+
+def learn_sparse_hybrid(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int, want_totals: bool = False,
+                        heavy_div: int = HEAVY_ROW_DIV):
+    """learn_sparse for heavy-tailed family sizes: annotations with more residues than S / heavy_div are COUNTED into
+    dense L2-resident rows (skm_rows_accumulate; their sequences gathered together), the others are sorted
+    (skm_learn_sparse_group); the two sorted lists are interleaved by annotation.  Same result as learn_sparse, bit for
+    bit.  want_totals: also return the Totals row (int64 [S], occurrences over ALL sequences, learn.smk:380) — the
+    unannotated sequences are then counted into a row of their own and the totals are column sums."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    S = code_space(tab.nsym, k)
+    ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    assert ann_id.numel() == batch.n
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    rows, heavy, rest_row = _learn_rows(batch, tab, k, ann_id, n_ann, S, want_totals, heavy_div) if batch.n and n_ann else (None, torch.zeros(0, dtype=torch.int64, device=dev), -1)
+    H = int(heavy.numel())
+    totals = torch.zeros(S, dtype=torch.int64, device=dev) if want_totals else None
+    # light part: the heavy annotations (and, with totals, nothing else) leave the sorted path
+    if H:
+        is_heavy = torch.zeros(n_ann + 1, dtype=torch.bool, device=dev)
+        is_heavy[heavy] = True
+        safe = torch.where((ann_id >= 0) & (ann_id < n_ann), ann_id, torch.full_like(ann_id, n_ann)).to(torch.int64)
+        ann_light = torch.where(is_heavy[safe], torch.full_like(ann_id, -1), ann_id)
+    else:
+        ann_light = ann_id
+    kl, vl = learn_sparse(batch, alphabet, k, ann_light, n_ann)
+    if want_totals:
+        check(lib().skm_coo_colsum(_ptr(kl), _ptr(vl), kl.numel(), S, _ptr(totals), _stream()))
+        if rows is not None:
+            check(lib().skm_rows_colsum(_ptr(rows), rows.shape[0], S, _ptr(totals), _stream()))
+        else:                                           # no row machinery (empty batch / no annotations): count the rest directly
+            rest = torch.nonzero((ann_id < 0) | (ann_id >= n_ann)).reshape(-1)
+            if rest.numel():
+                g_res, g_off = gather_sequences(batch, rest)
+                basis_accumulate(SequenceBatch(g_res, g_off, g_off.cpu().numpy()), alphabet, k, totals, None, 0)
+    if H == 0:
+        return (kl, vl, totals) if want_totals else (kl, vl)
+    # heavy part: non-zeros per block -> places -> emit
+    blk = lib().skm_rows_block()
+    nblk = (S + blk - 1) // blk
+    counts = torch.empty((H, nblk), dtype=torch.int32, device=dev)
+    check(lib().skm_rows_block_counts(_ptr(rows), H, S, _ptr(counts), _stream()))
+    c64 = counts.to(torch.int64)
+    incl = torch.cumsum(c64, dim=1)
+    blk_off = (incl - c64).contiguous()                  # exclusive inside a row
+    row_nnz = incl[:, -1].contiguous()
+    # where the heavy blocks go: position in the light list (entries of smaller annotations) + heavy entries before
+    ins_pos = torch.searchsorted(kl, heavy * S).contiguous()
+    cum = torch.cumsum(row_nnz, 0).contiguous()          # inclusive
+    row_dst = (ins_pos + cum - row_nnz).contiguous()
+    total = int(kl.numel()) + int(cum[-1].item())        # one sync
+    keys = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    vals = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    check(lib().skm_coo_shift_copy(_ptr(kl), _ptr(vl), kl.numel(), _ptr(ins_pos), _ptr(cum), H, _ptr(keys), _ptr(vals), _stream()))
+    check(lib().skm_rows_emit(_ptr(rows), H, S, _ptr(blk_off), _ptr(row_dst), _ptr(heavy.contiguous()), _ptr(keys), _ptr(vals), total, _stream()))
+    keys, vals = keys[:total], vals[:total]
+    return (keys, vals, totals) if want_totals else (keys, vals)
+
+
+def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int, method: str = "hybrid"):
     """learn_sparse + the Totals row (k-mer occurrences over ALL sequences, learn.smk:380) -> (keys, vals, totals int64 [S]).
-    The annotated share of the totals is the column sums of the matrix (one atomic per entry instead of one per
-    window); only the unannotated sequences are counted window by window."""
+    method "hybrid" (default): heavy annotations and the unannotated sequences are counted into dense rows, the Totals are
+    column sums (learn_sparse_hybrid).  "sorted": everything through the sort; the annotated share of the totals is the
+    column sums of the matrix (one atomic per entry instead of one per window) and the unannotated sequences are
+    counted window by window (the round-1 path, kept as the cross-check)."""
     tab = alphabet_tables(alphabet, batch.device)
     dev = batch.device
     S = code_space(tab.nsym, k)
     if S > _native.SKM_DENSE_MAX_SPACE:
         raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
     ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    if method == "hybrid":
+        return learn_sparse_hybrid(batch, alphabet, k, ann_id, n_ann, want_totals=True)
     keys, vals = learn_sparse(batch, alphabet, k, ann_id, n_ann)
     totals = torch.zeros(S, dtype=torch.int64, device=dev)
     check(lib().skm_coo_colsum(_ptr(keys), _ptr(vals), keys.numel(), S, _ptr(totals), _stream()))

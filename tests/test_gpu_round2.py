@@ -262,3 +262,42 @@ def test_vectorize_rule_beyond_the_dense_envelope(a, k, n, tmp_path):
     assert list(z["kmerlist"]) == list(r.kmerlist) and np.array_equal(z["vecs"], r.vecs())
     with pytest.raises(E.SkmError, match="rules_sparse"):
         R.learn_counts(ids, r.seqs, list(r.kmerlist), {})
+
+
+@pytest.mark.parametrize("a,k,n_seq,n_ann,zipf,frac_un,div", [
+    ("hydro", 10, 3000, 50, 1.1, 0.3, 4),       # S = 1024: almost every annotation is heavy
+    (2, 8, 4000, 300, 1.1, 0.3, 4),             # S = 6561: a heavy head, a light tail, adjacent heavy ids
+    (2, 8, 4000, 300, 0.0, 0.0, 4),             # uniform sizes: nothing heavy without the rest row
+    ("miqs", 3, 2000, 40, 1.5, 0.5, 1),         # S = 1000, threshold S: only the biggest families
+    (5, 4, 1500, 7, 1.1, 0.9, 4),               # few annotations, mostly unannotated
+    (2, 8, 600, 5, 1.1, 0.0, 1 << 30),          # threshold 0: EVERY annotation is heavy, the light list is empty
+])
+def test_learn_sparse_hybrid_equals_sorted(a, k, n_seq, n_ann, zipf, frac_un, div):
+    """Dense-row counting of the heavy annotations + sort of the light ones == the all-sorted path, bit for bit (keys,
+    values, Totals), and == the oracle's dense matrix."""
+    rng = np.random.default_rng(n_seq + n_ann)
+    seqs = _rand_seqs(rng, n_seq, 0, 300)
+    w = 1.0 / np.arange(1, n_ann + 1) ** zipf
+    ann = rng.permutation(n_ann)[rng.choice(n_ann, size=n_seq, p=w / w.sum())].astype(np.int32)      # heavy ids scattered
+    ann[rng.random(n_seq) < frac_un] = -1
+    ann[:3] = [n_ann + 5, -7, n_ann]                                      # ids outside [0, n_ann) count as unannotated
+    batch = E.SequenceBatch.from_strings(seqs)
+    d_ann = torch.from_numpy(ann)
+    k1, v1, t1 = E.learn_sparse_with_totals(batch, a, k, d_ann, n_ann, method="sorted")
+    k2, v2, t2 = E.learn_sparse_hybrid(batch, a, k, d_ann, n_ann, want_totals=True, heavy_div=div)
+    assert torch.equal(k1, k2) and torch.equal(v1, v2) and torch.equal(t1, t2)
+    k3, v3 = E.learn_sparse_hybrid(batch, a, k, d_ann, n_ann, want_totals=False, heavy_div=div)
+    assert torch.equal(k1, k3) and torch.equal(v1, v3)
+    lut, syms = O.build_lut(a)
+    S = len(syms) ** k
+    res, offs = O.pack(seqs)
+    si, pos, code, valid = O.window_codes(res, offs, lut, len(syms), k)
+    C = O.count_matrix(si, code, valid, n_seq, np.arange(S, dtype=np.uint64)).astype(np.int64)
+    M = np.zeros((n_ann, S), dtype=np.int64)
+    ok = (ann >= 0) & (ann < n_ann)
+    np.add.at(M, ann[ok], C[ok])
+    got = np.zeros_like(M)
+    kk = k2.cpu().numpy()
+    got[kk // S, kk % S] = v2.cpu().numpy()
+    assert np.array_equal(got, M) and np.array_equal(t2.cpu().numpy(), C.sum(axis=0))
+    assert bool((k2[1:] > k2[:-1]).all()) if k2.numel() > 1 else True
