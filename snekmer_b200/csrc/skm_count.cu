@@ -147,8 +147,6 @@ constexpr int CW_WARPS = 8;
 constexpr int CW_C = 12;                          // residues per lane and segment (4 * odd: conflict-free byte reads)
 constexpr int CW_SEG = 32 * CW_C;
 constexpr int CW_SYM = ts_sym_bytes(CW_SEG);      // 480
-constexpr size_t CW_ZPOOL = 1u << 20;             // zero-initialised device memory: L2-resident source of the bulk zero-fill (A/B variant)
-__device__ __align__(128) uint8_t g_cw_zero[CW_ZPOOL];
 
 // MAP: 0 = identity basis (column = code), 1 = col_of_code staged in shared memory as uint16 columns (S <= 16384;
 // filtered codes point at a dummy counter behind the row, so the scan needs no validity test), 2 = col_of_code read
@@ -316,24 +314,21 @@ count_dense_warp_bytes_kernel(const uint8_t *__restrict__ res, int64_t nres, con
 //     word, last word, an X somewhere in 192 bytes — and made the first word-based version execute MORE instructions);
 //   * positions are 32-bit offsets from the warp's own (16-byte aligned) base, and the offsets of 31 sequences are
 //     fetched with one coalesced load and handed out by shuffles;
-//   * a flushed row is re-zeroed by the copy engine (cp.async.bulk shared -> shared from a zero row of the CTA,
-//     completing on the warp's mbarrier while the next sequence is being staged) instead of 8 STS.128 per lane: the
-//     kernel is bound by the LSU wavefront pipe (85 % busy, the SRAM banks themselves 14 %), and zeroing was 32 of its
-//     189 wavefronts per sequence.  (ZFILL = 0 keeps the stores: rows that do not fit a second copy per CTA.)
-template <typename OutT, int MAP, bool ZFILL>
+// Measured and dropped (profiles/R2e_*): re-zeroing the flushed row with the copy engine instead of 8 STS.128 per lane
+// (zeroing is 32 of the 189 LSU wavefronts per sequence and the LSU wavefront pipe is what bounds the kernel: 85 % busy,
+// the SRAM banks 14 %).  cp.async.bulk shared -> shared from a zero row of the CTA on a per-warp mbarrier needs a
+// cluster launch (illegal instruction otherwise) and ran at 1.21 ms against 0.85 ms; global (L2) -> shared 0.92 ms.
+template <typename OutT, int MAP>
 __global__ void __launch_bounds__(32 * CW_WARPS, 6)
 count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int64_t *__restrict__ off, int64_t nseq,
                         const uint8_t *__restrict__ lut, uint32_t nsym, int k, uint32_t pow_k1,
                         const int32_t *__restrict__ col_of_code, int S, int K, uint32_t row_bytes, uint32_t map_bytes, int bulk_ok,
-                        OutT *__restrict__ out, const uint8_t *__restrict__ zsrc) {
+                        OutT *__restrict__ out) {
     extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ __align__(16) uint8_t s_lut[256];
-    __shared__ __align__(8) uint64_t s_bar[CW_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint16_t *s_col = reinterpret_cast<uint16_t *>(s_raw);                       // [S] when MAP == 1
     uint8_t *mine = s_raw + map_bytes + size_t(warp) * (row_bytes + CW_SYM);
-    uint4 *s_zero4 = reinterpret_cast<uint4 *>(s_raw + map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM));   // ZFILL: row_bytes of zeros
-    const uint32_t bar = smem_addr(&s_bar[warp]), zero_addr = smem_addr(s_zero4);
     uint4 *s_cnt4 = reinterpret_cast<uint4 *>(mine);
     uint8_t *s_res = mine + row_bytes;                                           // raw residue bytes of the segment
     uint32_t cnt_addr = smem_addr(mine), raw_addr = smem_addr(s_res), col_addr = smem_addr(s_col), lut_addr = smem_addr(s_lut);
@@ -347,14 +342,7 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
         }
     if (MAP == 1 && threadIdx.x == 0) s_col[S] = uint16_t(K);                   // entry S: where invalid windows go
     for (int i = lane; i < int(row_bytes >> 4); i += 32) s_cnt4[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (ZFILL) {
-        for (int i = threadIdx.x; i < int(row_bytes >> 4); i += blockDim.x) s_zero4[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (lane == 0) ts_mbar_init(bar, 1);
-        ts_bulk_fence();                                    // the zero row is read by the async proxy
-    }
-    __syncthreads();                                        // LUT, column map, zero row; the only CTA-wide barrier
-    uint32_t zphase = 0;
-    bool zpending = false;                                  // a zero-fill of this warp's row is in flight
+    __syncthreads();                                        // LUT and column map; the only CTA-wide barrier
     // this warp's sequences: those that start in the w-th 1/W of the residue buffer
     int64_t lo = 0, hi = 0;
     if (lane == 0) {
@@ -409,7 +397,6 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
                 if (first) { const int f0 = (lo_i & ~3) - 4; if (f0 + lane < lo_i) s_res[f0 + lane] = 0; }   // previous word + front of the first word
                 if (lane < ((4 - (hi_i & 3)) & 3)) s_res[hi_i + lane] = 0;
                 __syncwarp();
-                if (ZFILL && zpending) { ts_mbar_wait(bar, zphase); zphase ^= 1u; zpending = false; }   // the row is zero again
                 // lane owns cw words (cw odd -> conflict-free LDS.32) from word index w0
                 const int A = lo_i & ~3;
                 const int n = hi_i - A;
@@ -462,7 +449,6 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
             }
             // ---- flush: the row is one contiguous K * sizeof(OutT) range of the output ----
             OutT *dst = out + (s0 + i) * K;
-            if (ZFILL && zpending) { ts_mbar_wait(bar, zphase); zphase ^= 1u; zpending = false; }       // (a sequence without residues)
             if (bulk_ok) {
                 ts_bulk_fence();
                 __syncwarp();
@@ -474,19 +460,7 @@ count_dense_warp_kernel(const uint8_t *__restrict__ res, int64_t nres, const int
                 for (int j = lane; j < K; j += 32) dst[j] = s_cnt[j];
                 __syncwarp();
             }
-            if (ZFILL) {
-                if (s0 + i + 1 < hi) {                      // (nothing may be in flight into this CTA's memory when the warp exits)
-                    if (!bulk_ok) ts_bulk_fence();          // the plain-load flush above read the row through the generic proxy
-                    if (lane == 0) {
-                        ts_mbar_expect_tx(bar, row_bytes);
-                        if (zsrc) ts_bulk_copy_g2s(cnt_addr, zsrc + ((size_t(blockIdx.x) * CW_WARPS + warp) * 4096u) % (CW_ZPOOL - 16384u), row_bytes, bar);
-                        else ts_bulk_copy_s2s(cnt_addr, zero_addr, row_bytes, bar);
-                    }
-                    zpending = true;
-                }
-            } else {
-                for (int j = lane; j < int(row_bytes >> 4); j += 32) s_cnt4[j] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            for (int j = lane; j < int(row_bytes >> 4); j += 32) s_cnt4[j] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
         }
     }
@@ -573,18 +547,8 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
         const uint32_t map_bytes = map_mode == 1 ? uint32_t((size_t(S + 1) * 2 + 127) & ~size_t(127)) : 0u;     // + the entry for invalid windows
         const char *force_bytes = getenv("SKM_CDW_BYTES");                      // A/B switch: the byte-wise scan of round 1
         const bool words = k - 1 <= 4 && !(force_bytes && atoi(force_bytes));
-        const char *no_zfill = getenv("SKM_CDW_NOZFILL");                       // A/B switch: re-zero the row with stores
-        const char *zmode = getenv("SKM_CDW_ZFILL");                            // smem (default) | smem_nocluster | l2 | off
-        const bool zfill = words && !(no_zfill && atoi(no_zfill)) && !(zmode && !strcmp(zmode, "off"));
-        const bool zfill_cluster = zfill && !(zmode && !strcmp(zmode, "smem_nocluster"));   // shared -> shared bulk copies address shared::cluster: launch as a cluster of one
-        const uint8_t *zsrc = nullptr;
-        if (zfill && zmode && !strcmp(zmode, "l2")) {
-            void *sym = nullptr;
-            SKM_CUDA_TRY(cudaGetSymbolAddress(&sym, g_cw_zero));
-            zsrc = (const uint8_t *)sym;
-        }
-        const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM) + (zfill ? row_bytes : 0);
-        int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 512));
+        const size_t smem_w = map_bytes + size_t(CW_WARPS) * (row_bytes + CW_SYM);
+        int per_sm_w = int((227 * 1024) / (smem_w + 1024 + 256));
         if (per_sm_w > 6) per_sm_w = 6;
         if (per_sm_w < 1) per_sm_w = 1;
         const int grid_w = (int)std::min<int64_t>((nseq + CW_WARPS - 1) / CW_WARPS, int64_t(sm_count()) * per_sm_w);
@@ -597,16 +561,10 @@ int skm_count_dense(const uint8_t *d_residues, int64_t nres, const int64_t *d_of
             kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
                                                         d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok, (OUT *)d_counts); \
         } else {                                                                                                     \
-            auto kern = zfill ? count_dense_warp_kernel<OUT, MAP, true> : count_dense_warp_kernel<OUT, MAP, false>;  \
+            auto kern = count_dense_warp_kernel<OUT, MAP>;                                                           \
             SKM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));      \
-            cudaLaunchConfig_t cfg = {};                                                                             \
-            cfg.gridDim = dim3((unsigned)grid_w); cfg.blockDim = dim3(32 * CW_WARPS); cfg.dynamicSmemBytes = smem_w; cfg.stream = st; \
-            cudaLaunchAttribute attr[1];                                                                             \
-            attr[0].id = cudaLaunchAttributeClusterDimension;                                                        \
-            attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                \
-            cfg.attrs = attr; cfg.numAttrs = zfill_cluster ? 1 : 0;                                                  \
-            SKM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
-                                            d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok, (OUT *)d_counts, zsrc)); \
+            kern<<<grid_w, 32 * CW_WARPS, smem_w, st>>>(d_residues, nres, d_offsets, nseq, d_lut, (uint32_t)nsym, k, pow_k1, \
+                                                        d_col_of_code, (int)S, (int)K, row_bytes, map_bytes, bulk_ok, (OUT *)d_counts); \
         }                                                                                                            \
     }
 #define SKM_LAUNCH_DENSE_WM(OUT)                                                                                     \

@@ -289,38 +289,4 @@ __device__ __forceinline__ void ts_bulk_store(void *gdst, uint32_t ssrc, uint32_
 }
 __device__ __forceinline__ void ts_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// ---- bulk shared -> shared copy completing on an mbarrier (zero-fill of a counter row without LSU stores) --------
-__device__ __forceinline__ void ts_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void ts_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug surfaces as a launch failure, never as a hung GPU
-__device__ __forceinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x10000;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-// global -> this CTA's shared memory (16-byte aligned, bytes % 16 == 0), completing on the mbarrier
-__device__ __forceinline__ void ts_bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// dst / src: shared::cta addresses of this CTA, 16-byte aligned, bytes % 16 == 0
-__device__ __forceinline__ void ts_bulk_copy_s2s(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "r"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 }  // namespace skm
