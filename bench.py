@@ -1035,7 +1035,7 @@ def main():
         line, cpu = RUNNERS[args.workload](ctx, args, args.steps, args.warmup)
         if want_cpu and cpu is not None:
             line["cpu_baseline"] = cpu(cpu_sample)
-        if ctx.rank == 0:
+        if ctx.rank == 0 or ctx.world == 1:          # (RANK=1 WORLD_SIZE=1 reruns another rank's shard on one GPU)
             _emit(line)
         ctx.finish()
         return

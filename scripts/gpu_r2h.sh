@@ -1,0 +1,8 @@
+#!/bin/bash
+# R2h: N-rank run workload by workload with CUDA_LAUNCH_BLOCKING=1 to locate the fault of the N=2 default run.
+TAG=${1:-R2h}; N=${2:-2}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+for w in vectorize apply learn apply_sparse; do
+  CUDA_LAUNCH_BLOCKING=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 3 --warmup 3 --workload $w > $OUT/n${N}_$w.json 2> $OUT/n${N}_$w.err
+  rc=$?; echo "== $w N=$N rc=$rc"; cut -c1-400 $OUT/n${N}_$w.json
+  if [ $rc -ne 0 ]; then grep -v "^frame\|^$\|Search for\|might be incorrect\|TORCH_USE_CUDA_DSA\|CUDA_LAUNCH_BLOCKING" $OUT/n${N}_$w.err | grep -B30 "Error\|error" | head -90; fi
+done

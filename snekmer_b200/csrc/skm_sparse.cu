@@ -233,7 +233,10 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
             __syncthreads();
             int before = 0;
             for (int w = 0; w < warp; ++w) before += s_wtot[w];
-            if (tid <= nb) s_first[tid] = before + incl - nseg;          // tid == nb: the total
+            if (tid < nb) s_first[tid] = before + incl - nseg;
+            // the total: the LAST thread's inclusive prefix (with nb == SPA_EB == SPA_THREADS there is no thread `nb` that
+            // could write it — round 1 left s_first[SPA_EB] stale for queries with 512 or more distinct k-mers in a block)
+            if (tid == SPA_THREADS - 1) s_first[nb] = before + incl;
             __syncthreads();
             const int n_items = s_first[nb];
             // ---- walk: item t goes to warp t mod NW; a lane first finds (entry, segment) of one of its warp's next 32

@@ -301,3 +301,98 @@ def test_learn_sparse_hybrid_equals_sorted(a, k, n_seq, n_ann, zipf, frac_un, di
     got[kk // S, kk % S] = v2.cpu().numpy()
     assert np.array_equal(got, M) and np.array_equal(t2.cpu().numpy(), C.sum(axis=0))
     assert bool((k2[1:] > k2[:-1]).all()) if k2.numel() > 1 else True
+
+
+def _syn6():
+    from snekmer_b200 import alphabet as A
+
+    syn6 = {"AGILMV": "A", "FWY": "F", "NQSTC": "N", "DE": "D", "KRH": "K", "P": "P"}
+    A.register_alphabet("syn6", syn6)
+    return {"syn6": [(k, v) for k, v in syn6.items()]}
+
+
+def _uniref_like(rng, n, mean_len=350.0, sigma=0.6):
+    bg = dict(A=.122, L=.105, G=.084, R=.074, V=.071, D=.060, E=.057, P=.053, T=.050, S=.047, I=.047, F=.034, Q=.034,
+              K=.025, M=.024, N=.022, Y=.022, H=.021, W=.014, C=.009)
+    letters = np.array(list(bg) + ["X"])
+    p = np.append(np.array(list(bg.values())) / sum(bg.values()) * 0.999, 0.001)
+    lens = np.clip(np.rint(rng.lognormal(np.log(mean_len) - sigma * sigma / 2, sigma, size=n)), 30, 5000).astype(int)
+    return ["".join(rng.choice(letters, size=L, p=p)) for L in lens]
+
+
+def test_c3_shaped_learn_against_the_oracle():
+    """a C3-SHAPED learn (6-letter alphabet, k = 8, S = 1,679,616, Zipf(1.1) annotations, 30 % unannotated,
+    UniRef-like lengths) at a size the numpy oracle still does — 50,000 sequences, 2,000 annotations — compared with the
+    oracle's (annotation, k-mer) counts and Totals, for both device methods."""
+    extra = _syn6()
+    rng = np.random.default_rng(33)
+    n, n_ann, k = 50000, 2000, 8
+    seqs = _uniref_like(rng, n)
+    w = 1.0 / np.arange(1, n_ann + 1) ** 1.1
+    ann = rng.choice(n_ann, size=n, p=w / w.sum()).astype(np.int32)
+    ann[rng.random(n) < 0.3] = -1
+    lut, syms = O.build_lut("syn6", extra)
+    S = len(syms) ** k
+    res, offs = O.pack(seqs)
+    si, pos, code, valid = O.window_codes(res, offs, lut, len(syms), k)
+    a = ann[si]
+    keep = valid & (a >= 0)
+    want_k, want_v = np.unique(a[keep].astype(np.int64) * S + code[keep].astype(np.int64), return_counts=True)
+    want_t = np.bincount(code[valid].astype(np.int64), minlength=S)
+    batch = E.SequenceBatch.from_strings(seqs)
+    d_ann = torch.from_numpy(ann)
+    for method in ("hybrid", "sorted"):
+        keys, vals, totals = E.learn_sparse_with_totals(batch, "syn6", k, d_ann, n_ann, method=method)
+        assert np.array_equal(keys.cpu().numpy(), want_k), method
+        assert np.array_equal(vals.cpu().numpy(), want_v), method
+        assert np.array_equal(totals.cpu().numpy(), want_t), method
+
+
+def test_c4_shaped_sparse_apply_against_the_oracle():
+    """A C4-SHAPED apply (S = 1,679,616, matrix learned from Zipf families, half of the queries mutated copies of training
+    sequences): top-2 and scores of the SpMM path against exact sparse integer products (scipy) + float64 scaling."""
+    import scipy.sparse as sp
+
+    extra = _syn6()
+    rng = np.random.default_rng(44)
+    k, n_ann, n_train, nq = 8, 3000, 12000, 4000
+    train = _uniref_like(rng, n_train)
+    w = 1.0 / np.arange(1, n_ann + 1) ** 1.1
+    t_ann = rng.choice(n_ann, size=n_train, p=w / w.sum()).astype(np.int32)
+    queries = _uniref_like(rng, nq // 2)
+    aa = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+    for i in rng.choice(n_train, size=nq - nq // 2, replace=False):      # mutated copies: 10 % substitutions
+        s = np.array(list(train[int(i)]))
+        m = rng.random(len(s)) < 0.1
+        s[m] = rng.choice(aa, size=int(m.sum()))
+        queries.append("".join(s))
+    lut, syms = O.build_lut("syn6", extra)
+    S = len(syms) ** k
+
+    def csr_counts(seqs, rows_of=None, n_rows=None):
+        res, offs = O.pack(seqs)
+        si, pos, code, valid = O.window_codes(res, offs, lut, len(syms), k)
+        r = si[valid] if rows_of is None else rows_of[si[valid]]
+        m = sp.coo_matrix((np.ones(int(valid.sum()), dtype=np.int64), (r, code[valid].astype(np.int64))),
+                          shape=(len(seqs) if n_rows is None else n_rows, S)).tocsr()
+        m.sum_duplicates()
+        return m
+    M = csr_counts(train, t_ann, n_ann)
+    Q = csr_counts(queries)
+    dots = (Q @ M.T).toarray().astype(np.float64)                         # exact: integer products far below 2^53
+    qn = np.sqrt(np.asarray(Q.multiply(Q).sum(axis=1)).ravel().astype(np.float64))
+    mn = np.sqrt(np.asarray(M.multiply(M).sum(axis=1)).ravel().astype(np.float64))
+    qn[qn == 0] = 1.0
+    mn[mn == 0] = 1.0
+    Sc = dots / qn[:, None] / mn[None, :]
+    i1, i2, s1, s2 = O.top2(Sc)
+    tb = E.SequenceBatch.from_strings(train)
+    keys, vals = E.learn_sparse(tb, "syn6", k, torch.from_numpy(t_ann), n_ann)
+    qb = E.SequenceBatch.from_strings(queries)
+    rowptr, cols, cvals = E.count_csr(qb, "syn6", k, None)
+    r = E.apply_sparse_tiled(rowptr, cols, cvals, keys, vals, S, n_ann)
+    assert np.allclose(r.score1.cpu().numpy(), s1, rtol=1e-12, atol=1e-15) and np.allclose(r.score2.cpu().numpy(), s2, rtol=1e-12, atol=1e-15)
+    clear = (s1 - s2) > 1e-12 * np.maximum(s1, 1e-30)
+    assert np.array_equal(r.top1.cpu().numpy()[clear], i1[clear])
+    copies = np.arange(nq // 2, nq)
+    assert (r.score1.cpu().numpy()[copies] > 0.3).mean() > 0.9              # the mutated copies find their family
