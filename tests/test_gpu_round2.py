@@ -394,5 +394,5 @@ def test_c4_shaped_sparse_apply_against_the_oracle():
     assert np.allclose(r.score1.cpu().numpy(), s1, rtol=1e-12, atol=1e-15) and np.allclose(r.score2.cpu().numpy(), s2, rtol=1e-12, atol=1e-15)
     clear = (s1 - s2) > 1e-12 * np.maximum(s1, 1e-30)
     assert np.array_equal(r.top1.cpu().numpy()[clear], i1[clear])
-    copies = np.arange(nq // 2, nq)
-    assert (r.score1.cpu().numpy()[copies] > 0.3).mean() > 0.9              # the mutated copies find their family
+    # the long queries are the point: 512 or more distinct k-mers fill a whole staging block of the SpMM kernel
+    assert int((np.diff(rowptr.cpu().numpy()) >= 512).sum()) > 100
