@@ -489,18 +489,36 @@ def run_learn(ctx, args, steps, warmup):
     state, comm_ms = {}, []
     cev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
+    from snekmer_b200 import dist as D
+    phases = {"bounds": [], "all_to_all": [], "merge": [], "all_reduce_totals": []}
+    pev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
     def step(timed):
         keys, vals, count = E.learn_sparse_with_totals(batch, alphabet, k, d_ann, n_ann)     # matrix + Totals row over ALL sequences
         state["local_nnz"] = keys.numel()
         rng_ = (0, n_ann)
         if ctx.world > 1:
+            # E.exchange_coo_by_annotation, phase by phase (CUDA events on this stream; the NCCL work is ordered with it)
             if timed:
-                cev[0].record()
-            keys, vals, rng_ = E.exchange_coo_by_annotation(keys, vals, S, n_ann)
+                cev[0].record(); pev[0].record()
+            bounds = D.balanced_annotation_bounds(keys, S, n_ann)
+            if timed:
+                pev[1].record()
+            k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, [a * S for a in bounds], return_runs=True)
+            if timed:
+                pev[2].record()
+            keys, vals = E.coo_merge_runs(k2, v2, runs)
+            del k2, v2
+            if timed:
+                pev[3].record()
+            rng_ = (bounds[ctx.rank], bounds[ctx.rank + 1])
             dist.all_reduce(count)
             if timed:
+                pev[4].record()
                 cev[1].record(); cev[1].synchronize()
                 comm_ms.append(cev[0].elapsed_time(cev[1]))
+                for i, name in enumerate(phases):
+                    phases[name].append(pev[i].elapsed_time(pev[i + 1]))
         state.update(keys=keys, vals=vals, totals=count, range=rng_)
 
     total_ms, _ = ctx.timed(step, steps, warmup, clocks=False)
@@ -573,7 +591,9 @@ def run_learn(ctx, args, steps, warmup):
                       "parallelism": f"sequence-sharded x{ctx.world}"},
            "collective": ("all_reduce(per-annotation histogram) + all_to_all_single(COO keys, values by balanced annotation range) + merge tree + all_reduce(Totals)"
                           if ctx.world > 1 else None),
-           "comm_ms": c_ms, "local_ms": ms - c_ms, "parity_check": parity, "gpu_launches": launches * steps, "launches_per_step": names,
+           "comm_ms": c_ms, "local_ms": ms - c_ms,
+           "comm_phases_ms_this_rank": {n_: float(np.mean(v)) for n_, v in phases.items() if v} or None,
+           "parity_check": parity, "gpu_launches": launches * steps, "launches_per_step": names,
            "roofline": {"bound": "hbm", "kernel": "learn step (gather by annotation + per-slice 32-bit keys + sort + run-length encode + Totals)",
                         "achieved": alg_bytes / ((ms - c_ms) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                         "frac": alg_bytes / ((ms - c_ms) * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg_bytes, "kernel_ms": ms - c_ms,
@@ -654,11 +674,17 @@ def run_apply_sparse(ctx, args, steps, warmup):
     parity = "n/a (single rank): the tests compare this path with the dense float64 oracle"
     ok = True
     if ctx.world > 1:
-        bounds = D.balanced_annotation_bounds(keys, S, n_ann)
+        # annotation ranges balanced by what a slice costs in the SpMM: every entry weighted by how often its k-mer occurs
+        # (entry counts alone put the 613 largest families — half of the entries, most of the work — on one rank)
+        col_tot = torch.zeros(S, dtype=torch.int64, device=ctx.dev)
+        E.check(E.lib().skm_coo_colsum(keys.data_ptr(), vals.data_ptr(), keys.numel(), S, col_tot.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        bounds = D.balanced_annotation_bounds(keys, S, n_ann, weights=col_tot[keys % S])
+        del col_tot
         a_lo, a_hi = bounds[ctx.rank], bounds[ctx.rank + 1]
         mine = [E.csc_build(keys, vals, S, min(tile, a_hi - a0), a0) for a0 in range(a_lo, a_hi, tile)]
         max_len_all = int(ctx.max_over_ranks([float(batch.max_len)])[0])
         cm, res_sh = [], {}
+        ph = {"gather_csr": [], "score": [], "gather_top2_merge": []}
         sev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         nq_all = ctx.world * batch.n
 
@@ -687,6 +713,8 @@ def run_apply_sparse(ctx, args, steps, warmup):
             if timed:
                 sev[3].record(); sev[3].synchronize()
                 cm.append(sev[0].elapsed_time(sev[1]) + sev[2].elapsed_time(sev[3]))
+                ph["gather_csr"].append(sev[0].elapsed_time(sev[1])); ph["score"].append(sev[1].elapsed_time(sev[2]))
+                ph["gather_top2_merge"].append(sev[2].elapsed_time(sev[3]))
             res_sh["r"] = m
 
         sh_ms, _ = ctx.timed(step_sharded, steps, warmup, clocks=False)
@@ -695,9 +723,15 @@ def run_apply_sparse(ctx, args, steps, warmup):
         ok = bool(torch.equal(m.top1[q0:q1], r.top1) and torch.equal(m.score1[q0:q1], r.score1) and
                   torch.equal(m.score2[q0:q1], r.score2) and torch.equal(m.top2[q0:q1], r.top2))
         ok = ctx.all_ok(ok)
+        mine_ph = [float(np.mean(ph[n_])) for n_ in ("gather_csr", "score", "gather_top2_merge")]
+        t_ph = torch.tensor(mine_ph, dtype=torch.float64, device=ctx.dev)
+        all_ph = [torch.empty_like(t_ph) for _ in range(ctx.world)]
+        dist.all_gather(all_ph, t_ph)
         sh_ms, sh_comm = ctx.max_over_ranks([sh_ms, float(np.mean(cm))])
         sharded = {"ms_per_step": sh_ms / steps, "comm_ms": sh_comm, "value": ctx.world * nseq / (sh_ms / steps * 1e-3),
                    "annotation_ranges": bounds,
+                   "phases_ms_per_rank [gather_csr, score, gather_top2+merge]": [[round(x, 2) for x in t.tolist()] for t in all_ph],
+                   "note": "a rank that finishes its slice early waits in the top-2 all_gather: comm_ms includes that skew",
                    "collective": "all_gather(query CSR: row lengths, codes, counts) + all_gather(per-shard top-2 ids, scores) + 2-way merge (skm_top2_merge)"}
         parity = ("ok" if ok else "FAILED") + ": annotation-sharded top-2 (ids and float64 scores) of this rank's queries == the replicated-matrix result, bit for bit"
     e2e_ms = 0.0

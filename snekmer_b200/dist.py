@@ -179,14 +179,20 @@ def alltoall_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds
     return (out_k, out_v, recv_l) if return_runs else (out_k, out_v)
 
 
-def balanced_annotation_bounds(keys: torch.Tensor, S: int, n_ann: int) -> List[int]:
+def balanced_annotation_bounds(keys: torch.Tensor, S: int, n_ann: int, weights: Optional[torch.Tensor] = None) -> List[int]:
     """W+1 annotation indices cutting [0, n_ann) into contiguous ranges with ~equal numbers of COO entries summed over
     all ranks (`keys` = this rank's sorted keys ann * S + code).  One all_reduce of the per-annotation entry histogram;
-    identical on every rank.  Family sizes are Zipf-distributed: equal id ranges would give rank 0 most of the matrix."""
+    identical on every rank.  Family sizes are Zipf-distributed: equal id ranges would give rank 0 most of the matrix.
+    weights (int64 [nnz], optional): balance the SUM OF WEIGHTS per range instead of the entry count — e.g. how often an
+    entry's k-mer occurs, which is what an annotation slice costs in the scoring SpMM."""
     rank, w = world()
     dev = keys.device
-    edges = torch.arange(n_ann + 1, dtype=torch.int64, device=dev) * int(S)
-    per_ann = torch.diff(torch.searchsorted(keys, edges))                      # local entries of every annotation
+    if weights is None:
+        edges = torch.arange(n_ann + 1, dtype=torch.int64, device=dev) * int(S)
+        per_ann = torch.diff(torch.searchsorted(keys, edges))                  # local entries of every annotation
+    else:
+        per_ann = torch.zeros(n_ann, dtype=torch.int64, device=dev)
+        per_ann.index_add_(0, torch.div(keys, int(S), rounding_mode="floor"), weights.to(torch.int64))
     allreduce_sum_(per_ann)
     csum = torch.cumsum(per_ann, 0)
     total = int(csum[-1].item()) if n_ann else 0
