@@ -377,6 +377,35 @@ SKM_API int skm_pack_presence_bits(const void *d_counts, int64_t rows, int64_t c
 SKM_API int skm_rows_out_of_range_i32(const int32_t *d_X, int64_t rows, int64_t cols, int32_t lo, int32_t hi,
                               int32_t *d_rows_out, int64_t capacity, int64_t *d_n_out, skm_stream_t stream);
 
+/* Packed exchange format of a sorted COO list for the multi-GPU fan-in (Merge.merge_dataframes across ranks,
+ * learn.smk:467-494): word = key << count_bits | count — 8 instead of 16 bytes per entry through the all_to_all and
+ * the merge tree; words sort like keys.  skm_coo_pack sets *d_overflow (device int) when a count needs more than
+ * count_bits or a key more than 64 - count_bits bits (the caller then uses the unpacked path).
+ * skm_coo_merge_runs_packed: skm_coo_merge_runs for runs of packed words -> unpacked (keys, summed counts). */
+SKM_API int skm_coo_pack(const uint64_t *d_keys, const int64_t *d_vals, int64_t n, int count_bits, uint64_t *d_packed,
+                 int *d_overflow, skm_stream_t stream);
+SKM_API size_t skm_coo_merge_runs_packed_workspace(int64_t n, int n_runs);
+SKM_API int skm_coo_merge_runs_packed(const uint64_t *d_packed_in, const int64_t *run_offsets_host, int n_runs,
+                              int count_bits, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
+                              void *workspace, size_t workspace_bytes, skm_stream_t stream);
+
+/* Multi-GPU fan-in over NVLink peer memory (one process per GPU; Merge.merge_dataframes across ranks, learn.smk:467-494).
+ * The ONE exception to "the library never allocates": CUDA IPC exports whole allocations, so receive buffers are
+ * cudaMalloc'ed here.  skm_peer_alloc returns the buffer and its 64-byte IPC handle (send it to the peers through the
+ * host-side process group); skm_peer_open maps a peer's buffer into this process (enables peer access lazily);
+ * skm_peer_close / skm_peer_free undo them.  These four calls synchronise like cudaMalloc / cudaFree.
+ * skm_coo_pack_push: fused pack + all_to_all.  Entries [cut[r], cut[r+1]) of the local SORTED list (cut_host has world+1
+ * values) are packed (skm_coo_pack's word format) and stored directly into rank r's receive buffer at entry offset
+ * dst_off_host[r] (peer_bufs_host[r]; the own buffer for r == this rank).  The caller orders the step across ranks: a
+ * collective before the call (nobody still reads its buffer) and one after it (all stores have landed). */
+#define SKM_PEER_HANDLE_BYTES 64
+SKM_API int skm_peer_alloc(size_t bytes, void **d_ptr, void *handle_out);
+SKM_API int skm_peer_open(const void *handle, void **d_ptr);
+SKM_API int skm_peer_close(void *d_ptr);
+SKM_API int skm_peer_free(void *d_ptr);
+SKM_API int skm_coo_pack_push(const uint64_t *d_keys, const int64_t *d_vals, const int64_t *cut_host, int world, int count_bits,
+                      void *const *peer_bufs_host, const int64_t *dst_off_host, int *d_overflow, skm_stream_t stream);
+
 /* (a12) learn for the heavy annotations: dense count rows (learn.smk:306-326,385-408 when a few families own most of
  * the sequences).  d_rows is uint32 [n_rows, S] (S = nsym^k <= 2^27), zeroed by the caller.
  * skm_rows_accumulate: rows[row_of_seq[s]][code] += 1 for every valid window of sequence s; sequences with

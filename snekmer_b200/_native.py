@@ -92,6 +92,14 @@ SIGNATURES = {
     "skm_pack_presence_bits": (_int, [_p, _i64, _i64, _int, _p, _p]),
     "skm_rows_out_of_range_i32": (_int, [_p, _i64, _i64, C.c_int32, C.c_int32, _p, _i64, _p, _p]),
     "skm_bench_fma_f32": (_int, [_i64, _int, _p, C.POINTER(C.c_double), _p]),
+    "skm_coo_pack": (_int, [_p, _p, _i64, _int, _p, _p, _p]),
+    "skm_coo_merge_runs_packed_workspace": (_sz, [_i64, _int]),
+    "skm_coo_merge_runs_packed": (_int, [_p, _p, _int, _int, _p, _p, _p, _p, _sz, _p]),
+    "skm_peer_alloc": (_int, [_sz, C.POINTER(C.c_void_p), _p]),
+    "skm_peer_open": (_int, [_p, C.POINTER(C.c_void_p)]),
+    "skm_peer_close": (_int, [_p]),
+    "skm_peer_free": (_int, [_p]),
+    "skm_coo_pack_push": (_int, [_p, _p, _p, _int, _int, _p, _p, _p, _p]),
     "skm_rows_accumulate": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _p, _p]),
     "skm_rows_block": (_int, []),
     "skm_rows_block_counts": (_int, [_p, _i64, _i64, _p, _p]),

@@ -678,6 +678,109 @@ int skm_coo_merge_runs(const uint64_t *d_keys_in, const int64_t *d_vals_in, cons
     return SKM_OK;
 }
 
+// ---- packed exchange format: one 64-bit word per entry ---------------------------------------------------------------
+// word = key << count_bits | count.  Halves the bytes of the multi-GPU exchange (all_to_all + merge tree move 8 instead of
+// 16 bytes per entry) whenever the key (annotation * S + code) and the count fit 64 bits together; words sort like keys.
+namespace skm {
+__global__ void __launch_bounds__(256) coo_pack_kernel(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals, int64_t n,
+                                                       int count_bits, uint64_t *__restrict__ out, int *__restrict__ overflow) {
+    const uint64_t vmax = 1ull << count_bits, kmax = 1ull << (64 - count_bits);
+    bool bad = false;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const uint64_t k = keys[i], v = uint64_t(vals[i]);
+        bad |= (v >= vmax) | (k >= kmax);
+        out[i] = (k << count_bits) | (v & (vmax - 1));
+    }
+    if (bad) atomicOr(overflow, 1);
+}
+struct PackedKey {
+    int bits;
+    __host__ __device__ uint64_t operator()(uint64_t w) const { return w >> bits; }
+};
+struct PackedVal {
+    uint64_t mask;
+    __host__ __device__ int64_t operator()(uint64_t w) const { return int64_t(w & mask); }
+};
+}  // namespace skm
+
+int skm_coo_pack(const uint64_t *d_keys, const int64_t *d_vals, int64_t n, int count_bits, uint64_t *d_packed, int *d_overflow,
+                 skm_stream_t stream) {
+    using namespace skm;
+    if (n < 0 || count_bits < 1 || count_bits > 62 || !d_overflow) { set_error("skm_coo_pack: bad arguments"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_overflow, 0, sizeof(int), st));
+    if (n == 0) return SKM_OK;
+    if (!d_keys || !d_vals || !d_packed) { set_error("skm_coo_pack: NULL argument"); return SKM_ERR_INVALID; }
+    coo_pack_kernel<<<(int)std::min<int64_t>((n + 255) / 256, int64_t(sm_count()) * 16), 256, 0, st>>>(d_keys, d_vals, n, count_bits, d_packed, d_overflow);
+    SKM_LAUNCH_CHECK("coo_pack_kernel");
+    return SKM_OK;
+}
+
+size_t skm_coo_merge_runs_packed_workspace(int64_t n, int n_runs) {
+    using namespace skm;
+    if (n <= 0 || n_runs <= 0) return 256;
+    size_t t_m = 0, t_red = 0;
+    const int half = (int)std::min<int64_t>(n, (1ll << 31) - 1);
+    cub::DeviceMerge::MergeKeys(nullptr, t_m, (const uint64_t *)nullptr, half, (const uint64_t *)nullptr, half, (uint64_t *)nullptr);
+    cub::TransformInputIterator<uint64_t, PackedKey, const uint64_t *> ki((const uint64_t *)nullptr, PackedKey{1});
+    cub::TransformInputIterator<int64_t, PackedVal, const uint64_t *> vi((const uint64_t *)nullptr, PackedVal{1});
+    cub::DeviceReduce::ReduceByKey(nullptr, t_red, ki, (uint64_t *)nullptr, vi, (int64_t *)nullptr, (int64_t *)nullptr, cub::Sum(), n);
+    return 2 * al(size_t(n) * 8) + al(std::max(t_m, t_red)) + 1024;
+}
+
+int skm_coo_merge_runs_packed(const uint64_t *d_packed_in, const int64_t *run_offsets_host, int n_runs, int count_bits,
+                              uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out, void *workspace, size_t workspace_bytes,
+                              skm_stream_t stream) {
+    using namespace skm;
+    if (n_runs < 0 || !d_n_out || (n_runs > 0 && !run_offsets_host) || count_bits < 1 || count_bits > 62) { set_error("skm_coo_merge_runs_packed: bad arguments"); return SKM_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA_TRY(cudaMemsetAsync(d_n_out, 0, 8, st));
+    if (n_runs == 0) return SKM_OK;
+    const int64_t base0 = run_offsets_host[0], n = run_offsets_host[n_runs] - base0;
+    for (int r = 0; r < n_runs; ++r)
+        if (run_offsets_host[r + 1] < run_offsets_host[r]) { set_error("skm_coo_merge_runs_packed: run offsets must not decrease"); return SKM_ERR_INVALID; }
+    if (n == 0) return SKM_OK;
+    if (n >= (1ll << 31)) { set_error("skm_coo_merge_runs_packed: more than 2^31 entries"); return SKM_ERR_UNSUPPORTED; }
+    if (!d_packed_in || !d_keys_out || !d_vals_out) { set_error("skm_coo_merge_runs_packed: NULL argument"); return SKM_ERR_INVALID; }
+    const size_t need = skm_coo_merge_runs_packed_workspace(n, n_runs);
+    if (!workspace || workspace_bytes < need) { set_error("skm_coo_merge_runs_packed: workspace %zu < %zu", workspace_bytes, need); return SKM_ERR_WORKSPACE; }
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const size_t seg = al(size_t(n) * 8);
+    uint64_t *kb[2] = {(uint64_t *)p, (uint64_t *)(p + seg)};
+    void *temp = p + 2 * seg;
+    const size_t temp_cap = workspace_bytes - size_t((char *)temp - (char *)workspace);
+    std::vector<int64_t> cur(n_runs + 1);
+    for (int r = 0; r <= n_runs; ++r) cur[r] = run_offsets_host[r] - base0;
+    const uint64_t *src = d_packed_in + base0;
+    int flip = 0;
+    while (cur.size() > 2) {                              // pairwise merge tree over the packed words (they sort like keys)
+        std::vector<int64_t> next;
+        next.push_back(0);
+        uint64_t *dk = kb[flip];
+        const int runs = int(cur.size()) - 1;
+        for (int r = 0; r < runs; r += 2) {
+            const int64_t a0 = cur[r], a1 = cur[r + 1];
+            if (r + 1 < runs) {
+                const int64_t b1 = cur[r + 2];
+                size_t tb = temp_cap;
+                SKM_CUDA_TRY(cub::DeviceMerge::MergeKeys(temp, tb, src + a0, (int)(a1 - a0), src + a1, (int)(b1 - a1), dk + a0, ::cuda::std::less<>{}, st));
+                next.push_back(b1);
+            } else {
+                SKM_CUDA_TRY(cudaMemcpyAsync(dk + a0, src + a0, size_t(a1 - a0) * 8, cudaMemcpyDeviceToDevice, st));
+                next.push_back(a1);
+            }
+        }
+        cur.swap(next);
+        src = dk;
+        flip ^= 1;
+    }
+    cub::TransformInputIterator<uint64_t, PackedKey, const uint64_t *> ki(src, PackedKey{count_bits});
+    cub::TransformInputIterator<int64_t, PackedVal, const uint64_t *> vi(src, PackedVal{(1ull << count_bits) - 1});
+    size_t tb = temp_cap;
+    SKM_CUDA_TRY(cub::DeviceReduce::ReduceByKey(temp, tb, ki, d_keys_out, vi, d_vals_out, d_n_out, cub::Sum(), n, st));
+    return SKM_OK;
+}
+
 size_t skm_csc_build_workspace(int64_t nnz, int64_t n_ann) {
     using namespace skm;
     if (nnz <= 0) return 256 + al(size_t(std::max<int64_t>(n_ann, 1)) * 8);

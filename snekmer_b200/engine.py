@@ -16,6 +16,7 @@ Data layout in HBM
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -754,6 +755,33 @@ def coo_merge_runs(keys: torch.Tensor, vals: torch.Tensor, run_sizes: Sequence[i
     return ok[:m].clone(), ov[:m].clone()
 
 
+def coo_merge_runs_packed(packed_ptr: int, run_sizes: Sequence[int], count_bits: int, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """coo_merge_runs for SORTED runs of packed words (key << count_bits | count, skm_coo_pack's format) lying back to
+    back at device address `packed_ptr` (a peer-memory receive buffer).  Returns (keys, vals, n) with n a device scalar:
+    the first n entries are the merged list — the caller slices after its own synchronisation."""
+    dev = _require_cuda(device)
+    n = int(sum(run_sizes))
+    offs = np.zeros(len(run_sizes) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(run_sizes, dtype=np.int64), out=offs[1:])
+    ws_bytes = lib().skm_coo_merge_runs_packed_workspace(n, len(run_sizes))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ok = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    ov = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    dn = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().skm_coo_merge_runs_packed(packed_ptr, offs.ctypes.data, len(run_sizes), int(count_bits), _ptr(ok), _ptr(ov), _ptr(dn),
+                                          _ptr(ws), ws_bytes, _stream()))
+    return ok, ov, dn
+
+
+def coo_pack(keys: torch.Tensor, vals: torch.Tensor, count_bits: int) -> Tuple[torch.Tensor, bool]:
+    """(packed words int64, overflow) — skm_coo_pack; the single-GPU half of the exchange format (tests, side-cars)."""
+    dev = _require_cuda(keys.device)
+    out = torch.empty(keys.numel(), dtype=torch.int64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().skm_coo_pack(_ptr(keys.contiguous()), _ptr(vals.contiguous()), keys.numel(), int(count_bits), _ptr(out), _ptr(flag), _stream()))
+    return out, bool(flag.item())
+
+
 def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int,
                  max_chunk_res: int = 1 << 28, method: str = "grouped") -> Tuple[torch.Tensor, torch.Tensor]:
     """Annotation x k-mer count matrix as a COO list sorted by key = ann * S + code
@@ -1353,6 +1381,14 @@ def apply_dense_annotation_sharded(Q: torch.Tensor, M_local: torch.Tensor, ann_b
     return merge_top2(idx, sc)
 
 
+def peer_exchange_enabled(t: torch.Tensor) -> bool:
+    """The sparse-learn fan-in goes through NVLink peer memory when the ranks are CUDA processes of one node (NCCL
+    backend); SKM_EXCHANGE=nccl selects the all_to_all_single baseline."""
+    import torch.distributed as dist
+    return (t.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl" and dist.get_world_size() <= 16
+            and os.environ.get("SKM_EXCHANGE", "peer") != "nccl")
+
+
 def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int,
                                balance: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Tuple[int, int]]:
     """Multi-GPU fan-in of sparse learn: annotations are split into W contiguous ranges, rank r ends up with the merged
@@ -1370,6 +1406,19 @@ def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n
         ann_bounds = D.balanced_annotation_bounds(keys, S, n_ann)
     else:
         ann_bounds = [n_ann * r // w for r in range(w)] + [n_ann]
-    k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, [a * int(S) for a in ann_bounds], return_runs=True)
+    key_bounds = [a * int(S) for a in ann_bounds]
+    count_bits = 64 - max(int(n_ann) * int(S) - 1, 1).bit_length()
+    if peer_exchange_enabled(keys) and count_bits >= 16:
+        # fused pack + all_to_all over NVLink peer memory (skm_coo_pack_push); the histogram all_reduce above (or the
+        # barrier below) is the fence that says no rank still reads its receive buffer
+        if not balance:
+            D.barrier()
+        ptr, runs, flag = D.push_coo_by_key_range(keys, vals, key_bounds, count_bits)
+        k3, v3, dn = coo_merge_runs_packed(ptr, runs, count_bits, keys.device)
+        m, bad = torch.cat([dn, flag.to(torch.int64)]).tolist()
+        if not bad:
+            return k3[:m].clone(), v3[:m].clone(), (ann_bounds[rank], ann_bounds[rank + 1])
+        # a count beyond count_bits somewhere: the unpacked NCCL exchange below
+    k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, key_bounds, return_runs=True)
     k3, v3 = coo_merge_runs(k2, v2, runs)           # W sorted runs, one per sender: merge tree + reduce-by-key
     return k3, v3, (ann_bounds[rank], ann_bounds[rank + 1])

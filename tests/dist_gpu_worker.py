@@ -69,6 +69,25 @@ def main():
     cols = want_basis.astype(np.int64)         # the dense matrix only holds basis columns (count > min_filter)
     assert np.array_equal(got[a_lo:a_hi][:, cols], want_M[a_lo:a_hi]), "sparse learn exchange"
     assert np.array_equal(gotb[b_lo:b_hi][:, cols], want_M[b_lo:b_hi]), "balanced sparse learn exchange"
+    # the default exchange above went through NVLink peer memory (skm_coo_pack_push); the NCCL all_to_all baseline must
+    # give the same lists bit for bit, and so must a run whose counts do not fit the packed word (falls back inside)
+    assert E.peer_exchange_enabled(keys0), "peer exchange should be the default under NCCL"
+    import os
+    os.environ["SKM_EXCHANGE"] = "nccl"
+    kn, vn, rn = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)
+    os.environ["SKM_EXCHANGE"] = "peer"
+    assert rn == (b_lo, b_hi) and torch.equal(kn, kb) and torch.equal(vn, vb), "peer exchange != NCCL exchange"
+    big = vals0.clone()
+    if big.numel():
+        big[0] = 1 << 61
+    ko, vo, _ = E.exchange_coo_by_annotation(keys0, big, S, n_ann)
+    os.environ["SKM_EXCHANGE"] = "nccl"
+    ko2, vo2, _ = E.exchange_coo_by_annotation(keys0, big, S, n_ann)
+    os.environ["SKM_EXCHANGE"] = "peer"
+    assert torch.equal(ko, ko2) and torch.equal(vo, vo2), "overflow fallback of the peer exchange"
+    for _ in range(3):                                    # buffer reuse across steps (fences)
+        k4, v4, _ = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)
+        assert torch.equal(k4, kb) and torch.equal(v4, vb), "repeated peer exchange"
     if rank == 0:
         sizes = [sp[2] for sp in spans]
         print("balanced exchange entries per rank:", sizes)

@@ -109,6 +109,20 @@ def _worker(rank, world, port, tmp):
         tot = torch.tensor([int(rv.sum()), int(cnt.sum())])
         dist.all_reduce(tot)
         assert tot[0].item() == tot[1].item()                 # nothing lost, nothing duplicated
+        # ---- layout of the peer-memory exchange (push_plan) == the layout all_to_all_single produced -------------------
+        cutk = np.searchsorted(uk, bounds)
+        send = torch.from_numpy(np.diff(cutk).astype(np.int64))
+        mat = torch.empty(world * world, dtype=torch.int64)
+        dist.all_gather_into_tensor(mat, send)
+        dst_off, runs, words = D.push_plan(mat.numpy().reshape(world, world), rank)
+        assert int(runs.sum()) == rk.numel() and words >= rk.numel()
+        plans = [None] * world
+        dist.all_gather_object(plans, (dst_off.tolist(), send.tolist(), uk[cutk[0]:cutk[-1]].tolist()))
+        buf = np.full(int(runs.sum()), -1, dtype=np.int64)              # what the pushes of all ranks would leave in MY buffer
+        for s_, (offs_, send_, keys_) in enumerate(plans):
+            start = int(np.sum(send_[:rank]))
+            buf[offs_[rank]:offs_[rank] + send_[rank]] = keys_[start:start + send_[rank]]
+        assert np.array_equal(buf, rk.numpy())
         # ---- the same exchange with ranges balanced by entry count (Zipf-sized annotations) ------------------------
         zrng = np.random.default_rng(7 + rank)
         wz = 1.0 / np.arange(1, 41) ** 1.3

@@ -396,3 +396,39 @@ def test_c4_shaped_sparse_apply_against_the_oracle():
     assert np.array_equal(r.top1.cpu().numpy()[clear], i1[clear])
     # the long queries are the point: 512 or more distinct k-mers fill a whole staging block of the SpMM kernel
     assert int((np.diff(rowptr.cpu().numpy()) >= 512).sum()) > 100
+
+
+@pytest.mark.parametrize("n_runs,count_bits,n", [(1, 29, 5000), (2, 29, 40000), (5, 20, 30000), (8, 29, 100000), (3, 40, 0)])
+def test_packed_exchange_format_merges_like_the_unpacked_one(n_runs, count_bits, n):
+    """skm_coo_pack + skm_coo_merge_runs_packed (the multi-GPU fan-in's wire format: key << count_bits | count) against
+    numpy and against skm_coo_merge_runs on the unpacked lists; overflow of either field is flagged."""
+    rng = np.random.default_rng(n_runs * 1000 + count_bits)
+    key_bits = min(64 - count_bits, 36)
+    runs_k, runs_v = [], []
+    for r in range(n_runs):
+        m = int(rng.integers(0, 2 * n // n_runs + 1)) if n else 0
+        k = np.unique(rng.integers(0, 1 << key_bits, size=m, dtype=np.int64) // 3)       # collisions between runs
+        runs_k.append(k)
+        runs_v.append(rng.integers(1, 1 << min(count_bits - 4, 30), size=k.size, dtype=np.int64))
+    keys = torch.from_numpy(np.concatenate(runs_k)).cuda()
+    vals = torch.from_numpy(np.concatenate(runs_v)).cuda()
+    sizes = [int(k.size) for k in runs_k]
+    packed, bad = E.coo_pack(keys, vals, count_bits)
+    assert not bad
+    assert np.array_equal(packed.cpu().numpy().view(np.uint64), (keys.cpu().numpy().astype(np.uint64) << np.uint64(count_bits)) | vals.cpu().numpy().astype(np.uint64))
+    ok, ov, dn = E.coo_merge_runs_packed(packed.data_ptr(), sizes, count_bits, keys.device)
+    m = int(dn.item())
+    uk, inv = np.unique(np.concatenate(runs_k), return_inverse=True)
+    uv = np.zeros(uk.size, dtype=np.int64)
+    np.add.at(uv, inv, np.concatenate(runs_v))
+    assert m == uk.size and np.array_equal(ok[:m].cpu().numpy(), uk) and np.array_equal(ov[:m].cpu().numpy(), uv)
+    if keys.numel():
+        k2, v2 = E.coo_merge_runs(keys, vals, sizes)
+        assert torch.equal(k2, ok[:m]) and torch.equal(v2, ov[:m])
+        big = vals.clone()
+        big[-1] = 1 << count_bits
+        assert E.coo_pack(keys, big, count_bits)[1]
+        if count_bits > 28:
+            bigk = keys.clone()
+            bigk[0] = 1 << (64 - count_bits)
+            assert E.coo_pack(bigk, vals, count_bits)[1]
