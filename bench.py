@@ -494,8 +494,18 @@ def run_learn(ctx, args, steps, warmup):
     count_bits = 64 - (n_ann * S - 1).bit_length()
     pev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
+    lev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    local_ev_ms, wall_ms = [], []
+    if os.environ.get("SKM_PEER_WARM") and ctx.world > 1:           # experiment: peer mappings opened, exchange through NCCL
+        D.peer_buffers().ensure(1 << 27)
+
     def step(timed):
+        t_w = time.perf_counter()
+        if timed:
+            lev[0].record()
         keys, vals, count = E.learn_sparse_with_totals(batch, alphabet, k, d_ann, n_ann)     # matrix + Totals row over ALL sequences
+        if timed:
+            lev[1].record()
         state["local_nnz"] = keys.numel()
         rng_ = (0, n_ann)
         if ctx.world > 1:
@@ -533,6 +543,8 @@ def run_learn(ctx, args, steps, warmup):
                 comm_ms.append(cev[0].elapsed_time(cev[1]))
                 for i, name in enumerate(phases):
                     phases[name].append(pev[i].elapsed_time(pev[i + 1]))
+                local_ev_ms.append(lev[0].elapsed_time(lev[1]))
+                wall_ms.append((time.perf_counter() - t_w) * 1e3)
         state.update(keys=keys, vals=vals, totals=count, range=rng_)
 
     total_ms, _ = ctx.timed(step, steps, warmup, clocks=False)
@@ -610,6 +622,8 @@ def run_learn(ctx, args, steps, warmup):
                           if ctx.world > 1 else None),
            "comm_ms": c_ms, "local_ms": ms - c_ms,
            "comm_phases_ms_this_rank": {n_: float(np.mean(v)) for n_, v in phases.items() if v} or None,
+           "local_learn_ms_events_this_rank": [round(x, 3) for x in local_ev_ms] or None,
+           "step_wall_ms_this_rank": [round(x, 3) for x in wall_ms] or None,
            "parity_check": parity, "gpu_launches": launches * steps, "launches_per_step": names,
            "roofline": {"bound": "hbm", "kernel": "learn step (gather by annotation + per-slice 32-bit keys + sort + run-length encode + Totals)",
                         "achieved": alg_bytes / ((ms - c_ms) * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

@@ -72,7 +72,6 @@ def main():
     # the default exchange above went through NVLink peer memory (skm_coo_pack_push); the NCCL all_to_all baseline must
     # give the same lists bit for bit, and so must a run whose counts do not fit the packed word (falls back inside)
     assert E.peer_exchange_enabled(keys0), "peer exchange should be the default under NCCL"
-    import os
     os.environ["SKM_EXCHANGE"] = "nccl"
     kn, vn, rn = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)
     os.environ["SKM_EXCHANGE"] = "peer"
