@@ -389,6 +389,27 @@ SKM_API int skm_coo_merge_runs_packed(const uint64_t *d_packed_in, const int64_t
                               int count_bits, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t *d_n_out,
                               void *workspace, size_t workspace_bytes, skm_stream_t stream);
 
+/* (a12) learn for the light annotations, on chip: one CTA sorts one TASK in shared memory (skm_annsort.cu; learn.smk:306-326,
+ * 385-408).  The batch holds the sequences of the task annotations gathered in annotation order.  A task = the sequences
+ * [seq_lo, seq_hi) of one annotation restricted to the codes [code_lo, code_hi), with at most skm_ann_sort_cap() windows;
+ * tasks are listed in (annotation, code_lo) order and together produce ONE sorted COO list: task t writes its entries
+ * (ann * S + code, count) from d_out_base[t] + (entries of the tasks in front, d_task_prefix[t]) on — out_base lets the
+ * caller leave room for entries other paths produce (the dense rows of heavy annotations).  *d_total_out = entries of all
+ * tasks; d_totals (NULL or int64 [S]) += the counts per code; *d_overflow != 0: a task had more windows than the capacity
+ * (its output is then missing; the caller must recompute with smaller tasks).
+ * skm_ann_hist: d_hist[r][code / bin_width] (uint32 [n_rows, n_bins]) = windows of the sequences [seq_lo[r], seq_hi[r]) per
+ * code bin — what the caller cuts an annotation with more than the capacity into tasks with. */
+SKM_API int skm_ann_sort_cap(void);
+SKM_API int skm_ann_hist(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                 const int32_t *d_seq_lo, const int32_t *d_seq_hi, int64_t n_rows, uint32_t bin_width, int n_bins, uint32_t *d_hist,
+                 skm_stream_t stream);
+SKM_API size_t skm_ann_sort_workspace(int64_t n_tasks);
+SKM_API int skm_ann_sort(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq, const uint8_t *d_lut, int nsym, int k,
+                 const int32_t *d_seq_lo, const int32_t *d_seq_hi, const uint32_t *d_code_lo, const uint32_t *d_code_hi, const int64_t *d_ann,
+                 const int64_t *d_out_base, int64_t n_tasks, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t capacity,
+                 int64_t *d_task_prefix, int64_t *d_totals, int64_t *d_total_out, int *d_overflow, void *workspace, size_t workspace_bytes,
+                 skm_stream_t stream);
+
 /* Multi-GPU fan-in over NVLink peer memory (one process per GPU; Merge.merge_dataframes across ranks, learn.smk:467-494).
  * The ONE exception to "the library never allocates": CUDA IPC exports whole allocations, so receive buffers are
  * cudaMalloc'ed here.  skm_peer_alloc returns the buffer and its 64-byte IPC handle (send it to the peers through the

@@ -858,10 +858,11 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
 
 HEAVY_ROW_DIV = 4                # an annotation is "heavy" when it has more residues than S / HEAVY_ROW_DIV ...
 HEAVY_ROWS_MAX_BYTES = 8 << 30   # ... as long as the dense rows of all heavy annotations stay below this
+ROWS_L2_BYTES = int(os.environ.get("SKM_ROWS_L2_MB", "40")) << 20   # rows counted by one skm_rows_accumulate launch (L2-resident counters)
 
 
 def _learn_rows(batch: SequenceBatch, tab: AlphabetTables, k: int, ann_id: torch.Tensor, n_ann: int, S: int,
-                want_totals: bool, heavy_div: int):
+                want_totals: bool, heavy_div: int, min_res: int = 0, heavy_ids: Optional[torch.Tensor] = None):
     """Dense-row part of learn_sparse_hybrid: returns (rows uint32 [R, S], heavy annotation ids int64 [H] ascending,
     rest_row index or -1).  Rows 0..H-1 are the heavy annotations, row H (when want_totals) the unannotated sequences."""
     dev = batch.device
@@ -869,13 +870,16 @@ def _learn_rows(batch: SequenceBatch, tab: AlphabetTables, k: int, ann_id: torch
     valid = (ann_id >= 0) & (ann_id < n_ann)
     per_ann = torch.zeros(n_ann + 1, dtype=torch.int64, device=dev)
     per_ann.index_add_(0, torch.where(valid, ann_id, torch.full_like(ann_id, n_ann)).to(torch.int64), lens)
-    thr = max(S // max(int(heavy_div), 1), 1)
-    heavy_mask = per_ann[:n_ann] > thr
-    max_rows = max(int(HEAVY_ROWS_MAX_BYTES // (4 * S)) - 1, 0)
-    heavy = torch.nonzero(heavy_mask).reshape(-1)
-    if heavy.numel() > max_rows:                         # keep the largest ones
-        order = torch.argsort(per_ann[heavy], descending=True)[:max_rows]
-        heavy = torch.sort(heavy[order]).values
+    if heavy_ids is not None:                            # the caller chose the rows (ascending ids)
+        heavy = heavy_ids.to(device=dev, dtype=torch.int64)
+    else:
+        thr = max(S // max(int(heavy_div), 1), 1, int(min_res))
+        heavy_mask = per_ann[:n_ann] > thr
+        max_rows = max(int(HEAVY_ROWS_MAX_BYTES // (4 * S)) - 1, 0)
+        heavy = torch.nonzero(heavy_mask).reshape(-1)
+        if heavy.numel() > max_rows:                         # keep the largest ones
+            order = torch.argsort(per_ann[heavy], descending=True)[:max_rows]
+            heavy = torch.sort(heavy[order]).values
     H = int(heavy.numel())                               # one sync
     rest_row = H if want_totals else -1
     R = H + (1 if want_totals else 0)
@@ -894,13 +898,28 @@ def _learn_rows(batch: SequenceBatch, tab: AlphabetTables, k: int, ann_id: torch
         g_res, g_off = gather_sequences(batch, sel)
         g_row = row_of_seq[sel].contiguous()
         total = int(g_off[-1].item())
-        # < 2^32 residues per call: chunk by sequences when a shard is larger
-        bounds = [0, sel.numel()]
-        if total >= (1 << 32) - 64:
-            step = max(1, sel.numel() // (total // ((1 << 31)) + 1))
-            bounds = list(range(0, sel.numel(), step)) + [sel.numel()]
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
-            e0, e1 = (int(x) for x in g_off[torch.tensor([lo, hi], device=dev)].tolist())
+        # One launch per group of rows whose counters fit L2 together (ROWS_L2_BYTES): a launch spreads its CTAs over the
+        # whole residue range it is given, so a single launch over all rows touches every row at once (C3: 66 rows =
+        # 442 MB) and the atomics run at DRAM speed.  Also < 2^32 residues per call.
+        per_launch = max(int(ROWS_L2_BYTES // (4 * S)), 1)
+        row_edges = torch.searchsorted(g_row, torch.arange(R + 1, dtype=torch.int32, device=dev)).tolist()
+        g_off_host = None
+        bounds = [0]
+        for r0 in range(0, R, per_launch):
+            lo, hi = row_edges[r0], row_edges[min(r0 + per_launch, R)]
+            if hi == lo:
+                continue
+            if total >= (1 << 32) - 64:                  # a huge group: cut it by sequences
+                if g_off_host is None:
+                    g_off_host = g_off.cpu().numpy()
+                while g_off_host[hi] - g_off_host[bounds[-1]] >= (1 << 31):
+                    bounds.append(int(np.searchsorted(g_off_host, g_off_host[bounds[-1]] + (1 << 31), side="right")) - 1)
+            bounds.append(hi)
+        edges = g_off[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
+        for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+            if hi == lo:
+                continue
+            e0, e1 = edges[i], edges[i + 1]
             base = e0 & ~15
             offs = (g_off[lo:hi + 1] - base).contiguous()
             check(lib().skm_rows_accumulate(_ptr(g_res[base:]), e1 - base, _ptr(offs), hi - lo, _ptr(tab.lut), tab.nsym, int(k),
@@ -967,7 +986,161 @@ def learn_sparse_hybrid(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Te
     return (keys, vals, totals) if want_totals else (keys, vals)
 
 
-def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int, method: str = "hybrid"):
+ONCHIP_HEAVY_SCALE = float(os.environ.get("SKM_ONCHIP_HEAVY_SCALE", "0.75"))   # dense rows beyond scale * sqrt(task capacity * S) residues
+ONCHIP_FILL = 0.8                                                      # target fill of a task cut from the code histogram
+
+
+def _hist_bins(nsym: int, k: int, S: int) -> Tuple[int, int]:
+    """(n_bins, bin_width) of the per-annotation code histogram: the leading j symbols of a code, nsym^j <= 8192."""
+    j = 0
+    while j < k and nsym ** (j + 1) <= 8192:
+        j += 1
+    return nsym ** j, nsym ** (k - j)
+
+
+def learn_sparse_onchip(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int, want_totals: bool = False,
+                        heavy_scale: float = ONCHIP_HEAVY_SCALE):
+    """learn_sparse without a device-wide sort.  Annotations with more than heavy_scale * sqrt(task capacity * S) residues
+    (where a dense row of S counters — ~20 bytes of traffic per code — costs less than the n^2 / capacity window scans of
+    the tasks the annotation would be cut into; C3: 158 k residues) are
+    counted into dense L2-resident rows (skm_rows_*); every other annotation is sorted ON CHIP by skm_ann_sort: one CTA
+    per task (annotation x code range, at most skm_ann_sort_cap() windows) scans, radix-sorts and run-length-encodes in
+    shared memory and writes its entries at their final place of the one sorted COO list.  Annotations larger than a task
+    are cut into code ranges from an exact histogram (skm_ann_hist).  Same result as learn_sparse, bit for bit; falls
+    back to learn_sparse_hybrid when a histogram bin alone exceeds a task (degenerate low-complexity input).
+    want_totals: also the Totals row (learn.smk:380)."""
+    tab = alphabet_tables(alphabet, batch.device)
+    dev = batch.device
+    S = code_space(tab.nsym, k)
+    ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    assert ann_id.numel() == batch.n
+    if S > _native.SKM_DENSE_MAX_SPACE:
+        raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
+    if batch.n == 0 or n_ann == 0:
+        return learn_sparse_hybrid(batch, alphabet, k, ann_id, n_ann, want_totals=want_totals)
+    T = int(lib().skm_ann_sort_cap())
+    thr = max(T, int(heavy_scale * (float(T) * float(S)) ** 0.5))
+    max_rows = max(int(HEAVY_ROWS_MAX_BYTES // (4 * S)) - 1, 0)
+    ok_id = (ann_id >= 0) & (ann_id < n_ann)
+    safe = torch.where(ok_id, ann_id, torch.full_like(ann_id, n_ann)).to(torch.int64)
+    lens = batch.offsets[1:] - batch.offsets[:-1]
+    per_ann = torch.zeros(n_ann + 1, dtype=torch.int64, device=dev)
+    per_ann.index_add_(0, safe, lens)
+    heavy = torch.nonzero(per_ann[:n_ann] > thr).reshape(-1)
+    if heavy.numel() > max_rows:                                      # keep the largest ones as rows
+        heavy = torch.sort(heavy[torch.argsort(per_ann[heavy], descending=True)[:max_rows]]).values
+    # ---- task annotations: sequences gathered in annotation order -------------------------------------------------------
+    is_heavy = torch.zeros(n_ann + 1, dtype=torch.bool, device=dev)
+    is_heavy[heavy] = True
+    key = torch.where(ok_id & ~is_heavy[safe], ann_id, torch.full_like(ann_id, n_ann))
+    sk, order = torch.sort(key, stable=True)
+    uniq, per = torch.unique_consecutive(sk, return_counts=True)
+    if uniq.numel() and int(uniq[-1].item()) == n_ann:                # the unselected sequences sort last
+        uniq, per = uniq[:-1], per[:-1]
+    A = int(uniq.numel())
+    n_tasks = 0
+    if A:
+        seq_hi = torch.cumsum(per, 0)
+        seq_lo = seq_hi - per
+        n_sel = int(seq_hi[-1].item())
+        g_res, g_off = gather_sequences(batch, order[:n_sel])
+        nres_g = int(g_off[-1].item())
+        ares = g_off[seq_hi] - g_off[seq_lo]                          # residues per task annotation
+        medium = ares > T
+        mi = torch.nonzero(medium).reshape(-1)
+        M = int(mi.numel())
+        t_ann = [uniq[~medium].to(torch.int64)]
+        t_lo, t_hi = [seq_lo[~medium]], [seq_hi[~medium]]
+        t_c0 = [torch.zeros(A - M, dtype=torch.int64, device=dev)]
+        t_c1 = [torch.full((A - M,), S, dtype=torch.int64, device=dev)]
+        if M:
+            n_bins, width = _hist_bins(tab.nsym, k, S)
+            hist = torch.empty((M, n_bins), dtype=torch.int32, device=dev)
+            m_lo, m_hi = seq_lo[mi].to(torch.int32).contiguous(), seq_hi[mi].to(torch.int32).contiguous()
+            check(lib().skm_ann_hist(_ptr(g_res), nres_g, _ptr(g_off), n_sel, _ptr(tab.lut), tab.nsym, int(k), _ptr(m_lo), _ptr(m_hi), M,
+                                     width, n_bins, _ptr(hist), _stream()))
+            fill = int(T * ONCHIP_FILL)
+            # an annotation with one bin beyond what a task can absorb (low-complexity families) gets a dense row instead
+            hot = hist.max(dim=1).values.to(torch.int64) > T - fill
+            n_hot = int(hot.sum().item())
+            if n_hot:
+                heavy = torch.sort(torch.cat([heavy, uniq[mi][hot].to(torch.int64)])).values
+                if heavy.numel() > max_rows:
+                    return learn_sparse_hybrid(batch, alphabet, k, ann_id, n_ann, want_totals=want_totals)
+                keep = torch.nonzero(~hot).reshape(-1)
+                mi, hist = mi[keep], hist[keep]
+                M = int(mi.numel())
+        if M:
+            h64 = hist.to(torch.int64)
+            cum = torch.cumsum(h64, 1)
+            q = torch.div((cum - 1).clamp_(min=0), fill, rounding_mode="floor")
+            start = torch.ones_like(q, dtype=torch.bool)
+            start[:, 1:] = q[:, 1:] != q[:, :-1]
+            rb = torch.nonzero(start)                                 # (medium row, first bin) of every task, row-major
+            r_, b_ = rb[:, 0], rb[:, 1]
+            b_hi = torch.full_like(b_, n_bins)
+            b_hi[:-1] = torch.where(r_[1:] == r_[:-1], b_[1:], b_hi[:-1])
+            t_ann.append(uniq[mi][r_].to(torch.int64))
+            t_lo.append(seq_lo[mi][r_])
+            t_hi.append(seq_hi[mi][r_])
+            t_c0.append(b_ * width)
+            t_c1.append(torch.clamp(b_hi * width, max=S))
+        t_ann, t_lo, t_hi, t_c0, t_c1 = (torch.cat(x) for x in (t_ann, t_lo, t_hi, t_c0, t_c1))
+        perm = torch.argsort(t_ann * (S + 1) + t_c0)
+        t_ann = t_ann[perm].contiguous()
+        t_lo, t_hi = t_lo[perm].to(torch.int32).contiguous(), t_hi[perm].to(torch.int32).contiguous()
+        t_c0, t_c1 = t_c0[perm].to(torch.int32).contiguous(), t_c1[perm].to(torch.int32).contiguous()     # uint32 patterns (S <= 2^27)
+        n_tasks = int(t_ann.numel())
+    # ---- heavy rows (+ the row of the unannotated sequences): counted, then entries per row -------------------------------
+    rows, heavy, rest_row = _learn_rows(batch, tab, k, ann_id, n_ann, S, want_totals, heavy_div=S + 1, heavy_ids=heavy)
+    H = int(heavy.numel())
+    totals = torch.zeros(S, dtype=torch.int64, device=dev) if want_totals else None
+    if H:
+        blk = lib().skm_rows_block()
+        nblk = (S + blk - 1) // blk
+        counts = torch.empty((H, nblk), dtype=torch.int32, device=dev)
+        check(lib().skm_rows_block_counts(_ptr(rows), H, S, _ptr(counts), _stream()))
+        c64 = counts.to(torch.int64)
+        incl = torch.cumsum(c64, dim=1)
+        blk_off = (incl - c64).contiguous()
+        row_nnz = incl[:, -1].contiguous()
+        heavy_cum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(row_nnz, 0)])    # exclusive, H + 1
+    else:
+        heavy_cum = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n_tasks:
+        out_base = heavy_cum[torch.searchsorted(heavy, t_ann)].contiguous() if H else torch.zeros(n_tasks, dtype=torch.int64, device=dev)
+    heavy_total = int(heavy_cum[-1].item()) if H else 0
+    capacity = heavy_total + (nres_g if A else 0)
+    keys = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
+    vals = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
+    task_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if n_tasks:
+        task_prefix = torch.empty(n_tasks, dtype=torch.int64, device=dev)
+        ws_bytes = lib().skm_ann_sort_workspace(n_tasks)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().skm_ann_sort(_ptr(g_res), nres_g, _ptr(g_off), n_sel, _ptr(tab.lut), tab.nsym, int(k), _ptr(t_lo), _ptr(t_hi), _ptr(t_c0),
+                                 _ptr(t_c1), _ptr(t_ann), _ptr(out_base), n_tasks, _ptr(keys), _ptr(vals), capacity, _ptr(task_prefix),
+                                 _ptr(totals), _ptr(task_total), _ptr(flag), _ptr(ws), ws_bytes, _stream()))
+    if rows is not None and want_totals:
+        check(lib().skm_rows_colsum(_ptr(rows), rows.shape[0], S, _ptr(totals), _stream()))
+    if H:
+        # a heavy annotation's block starts after its own heavy predecessors and after the task entries of smaller annotations
+        if n_tasks:
+            tp = torch.cat([task_prefix, task_total])
+            row_dst = (heavy_cum[:-1] + tp[torch.searchsorted(t_ann, heavy)]).contiguous()
+        else:
+            row_dst = heavy_cum[:-1].contiguous()
+        check(lib().skm_rows_emit(_ptr(rows), H, S, _ptr(blk_off), _ptr(row_dst), _ptr(heavy.contiguous()), _ptr(keys), _ptr(vals), capacity, _stream()))
+    n_task_entries, bad = torch.cat([task_total, flag.to(torch.int64)]).tolist()          # one sync
+    if bad:
+        return learn_sparse_hybrid(batch, alphabet, k, ann_id, n_ann, want_totals=want_totals)
+    total = heavy_total + n_task_entries
+    keys, vals = keys[:total], vals[:total]
+    return (keys, vals, totals) if want_totals else (keys, vals)
+
+
+def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int, method: Optional[str] = None):
     """learn_sparse + the Totals row (k-mer occurrences over ALL sequences, learn.smk:380) -> (keys, vals, totals int64 [S]).
     method "hybrid" (default): heavy annotations and the unannotated sequences are counted into dense rows, the Totals are
     column sums (learn_sparse_hybrid).  "sorted": everything through the sort; the annotated share of the totals is the
@@ -979,6 +1152,9 @@ def learn_sparse_with_totals(batch: SequenceBatch, alphabet, k: int, ann_id: tor
     if S > _native.SKM_DENSE_MAX_SPACE:
         raise SkmError(-3, f"code space {tab.nsym}^{k} exceeds the table limit 2^27")
     ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
+    method = method or os.environ.get("SKM_LEARN_METHOD", "hybrid")
+    if method == "onchip":
+        return learn_sparse_onchip(batch, alphabet, k, ann_id, n_ann, want_totals=True)
     if method == "hybrid":
         return learn_sparse_hybrid(batch, alphabet, k, ann_id, n_ann, want_totals=True)
     keys, vals = learn_sparse(batch, alphabet, k, ann_id, n_ann)

@@ -432,3 +432,52 @@ def test_packed_exchange_format_merges_like_the_unpacked_one(n_runs, count_bits,
             bigk = keys.clone()
             bigk[0] = 1 << (64 - count_bits)
             assert E.coo_pack(bigk, vals, count_bits)[1]
+
+
+@pytest.mark.parametrize("a,k,n_seq,n_ann,zipf,frac_un,scale", [
+    ("hydro", 10, 3000, 50, 1.1, 0.3, 0.75),     # S = 1024: everything above one task is a dense row
+    (2, 8, 4000, 300, 1.1, 0.3, 0.75),           # S = 6561: heavy head, small tail
+    (2, 8, 4000, 300, 0.0, 0.0, 0.75),           # uniform sizes: small tasks only
+    ("syn6", 8, 3000, 40, 1.1, 0.2, 10.0),       # S = 1,679,616, no dense rows: the head is cut into code-range tasks
+    ("syn6", 8, 3000, 40, 1.1, 0.2, 1e-6),       # same data, everything above one task is a dense row
+    ("syn6", 8, 2500, 3, 0.0, 0.0, 0.75),        # three annotations of ~125 k residues each: histogram-cut tasks
+    (5, 4, 1500, 7, 1.1, 0.9, 0.75),             # few annotations, mostly unannotated
+    ("miqs", 3, 50, 60, 0.0, 0.0, 0.75),         # more annotations than sequences: empty annotations
+])
+def test_learn_sparse_onchip_equals_sorted(a, k, n_seq, n_ann, zipf, frac_un, scale):
+    """skm_ann_sort / skm_ann_hist (one CTA sorts one annotation x code-range task in shared memory, decoupled look-back
+    for the output places) + dense rows for the heavy annotations == the all-sorted path, bit for bit (keys, values,
+    Totals)."""
+    if a == "syn6":
+        _syn6()
+    rng = np.random.default_rng(n_seq + n_ann)
+    seqs = _rand_seqs(rng, n_seq, 0, 300)
+    w = 1.0 / np.arange(1, n_ann + 1) ** zipf
+    ann = rng.permutation(n_ann)[rng.choice(n_ann, size=n_seq, p=w / w.sum())].astype(np.int32)
+    ann[rng.random(n_seq) < frac_un] = -1
+    ann[:3] = [n_ann + 5, -7, n_ann]
+    batch = E.SequenceBatch.from_strings(seqs)
+    d_ann = torch.from_numpy(ann)
+    k1, v1, t1 = E.learn_sparse_with_totals(batch, a, k, d_ann, n_ann, method="sorted")
+    k2, v2, t2 = E.learn_sparse_onchip(batch, a, k, d_ann, n_ann, want_totals=True, heavy_scale=scale)
+    assert k1.numel() == k2.numel(), (k1.numel(), k2.numel())
+    assert torch.equal(k1, k2) and torch.equal(v1, v2) and torch.equal(t1, t2)
+    k3, v3 = E.learn_sparse_onchip(batch, a, k, d_ann, n_ann, want_totals=False, heavy_scale=scale)
+    assert torch.equal(k1, k3) and torch.equal(v1, v3)
+
+
+def test_learn_sparse_onchip_degenerate_inputs():
+    """Low-complexity families (one histogram bin larger than a task -> the sorted fallback), windows shorter than k,
+    invalid residues only, an empty batch."""
+    _syn6()
+    rng = np.random.default_rng(5)
+    seqs = ["A" * 400] * 120 + ["AG" * 150] * 40 + _rand_seqs(rng, 300, 0, 200) + ["X" * 50, "AGI", ""]
+    ann = np.array([0] * 120 + [1] * 40 + list(rng.integers(0, 6, size=300)) + [2, 3, 4], dtype=np.int32)
+    batch = E.SequenceBatch.from_strings(seqs)
+    for scale in (10.0, 0.75):
+        k1, v1, t1 = E.learn_sparse_with_totals(batch, "syn6", 8, torch.from_numpy(ann), 6, method="sorted")
+        k2, v2, t2 = E.learn_sparse_onchip(batch, "syn6", 8, torch.from_numpy(ann), 6, want_totals=True, heavy_scale=scale)
+        assert torch.equal(k1, k2) and torch.equal(v1, v2) and torch.equal(t1, t2)
+    empty = E.SequenceBatch.from_strings([])
+    k0, v0, t0 = E.learn_sparse_onchip(empty, "syn6", 8, torch.zeros(0, dtype=torch.int32), 6, want_totals=True)
+    assert k0.numel() == 0 and v0.numel() == 0 and int(t0.sum().item()) == 0
