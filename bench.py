@@ -73,6 +73,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        """index: a GPU index or a comma-separated list — ONE nvidia-smi process samples all of them (the profiling recipe's
+        clocks line); one process per rank polling the driver every 100 ms perturbed 1-ms steps at 8 ranks."""
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
@@ -183,8 +185,21 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.cpus, self.all_cpus = None, os.sched_getaffinity(0)
+        if not os.environ.get("SKM_NO_CPU_BIND"):
+            from snekmer_b200 import dist as D
+            self.cpus = D.bind_to_local_cpus(self.local_rank)     # pinned buffers NUMA-local to this rank's GPU
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+
+    def run_cpu(self, cpu, sample):
+        """The CPU baseline leg uses ALL host cores (its worker processes inherit the affinity), not only the GPU-local ones."""
+        os.sched_setaffinity(0, self.all_cpus)
+        try:
+            return cpu(sample)
+        finally:
+            if self.cpus:
+                os.sched_setaffinity(0, self.cpus)
 
     def barrier(self):
         if self.world > 1:
@@ -206,7 +221,8 @@ class Ctx:
     def timed(self, step, steps, warmup, clocks=True):
         """warm-up, then EXACTLY `steps` steps between barrier+sync pairs; returns total ms (this rank) and clocks."""
         torch = self.torch
-        sampler = ClockSampler(self.local_rank) if clocks else None
+        # rank 0 samples the GPUs of ALL ranks (median clock over all samples, union of the throttle reasons)
+        sampler = ClockSampler(",".join(str(i) for i in range(self.world))) if clocks and self.rank == 0 else None
         if sampler:
             sampler.start()                  # nvidia-smi needs ~100 ms per sample: it runs from the warm-up on
         for _ in range(max(warmup, 3)):
@@ -219,15 +235,16 @@ class Ctx:
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
-        if not sampler:
+        if not clocks:
             return ms, None
         # a timed region of a few ms is over before the first sample: keep the same work running (untimed) until the
-        # sampler has seen the clocks under this load
-        t_end = time.time() + 2.0
-        while len(sampler.lines) < 5 and time.time() < t_end:
+        # sampler has seen the clocks under this load — at N > 1 on EVERY rank for a fixed time, so that the one sampler
+        # (rank 0) sees all GPUs under the load of the step
+        t_end = time.time() + (2.0 if self.world == 1 else 0.7)
+        while time.time() < t_end and (self.world > 1 or len(sampler.lines) < 5):
             step(False)
             torch.cuda.synchronize()
-        return ms, sampler.stop()
+        return ms, (sampler.stop() if sampler else None)
 
     def count_launches(self, step, fallback):
         """Kernels launched by ONE step, counted from a CUPTI trace of an extra untimed step (torch.profiler sees every
@@ -363,6 +380,7 @@ def run_vectorize(ctx, args, steps, warmup):
         m = e2e["uint8"]
         line["e2e"] = {"value": m["value"], "unit": "sequences/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": m["h2d_bytes_per_step"],
                        "d2h_bytes_per_step": m["d2h_bytes_per_step"], "pcie_gbs_per_rank": m["pcie_gbs_per_rank"],
+                       "cpu_affinity_rank0": (f"{len(ctx.cpus)} CPUs local to the GPU (NVML): {ctx.cpus[0]}..{ctx.cpus[-1]}" if ctx.cpus else "not bound"),
                        "api": "snekmer_b200.pipeline.vectorize_host(transport='uint8'): pinned host residues/offsets -> pinned host uint8 "
                               "counts [N, K] + escape list (row, col, count) of the entries >= 255; lossless",
                        "transports": {"uint16 (2 B per count, lossless below 65,536 residues per sequence)": e2e["uint16"],
@@ -1104,14 +1122,14 @@ def main():
     if args.workload != "all":
         line, cpu = RUNNERS[args.workload](ctx, args, args.steps, args.warmup)
         if want_cpu and cpu is not None:
-            line["cpu_baseline"] = cpu(cpu_sample)
+            line["cpu_baseline"] = ctx.run_cpu(cpu, cpu_sample)
         if ctx.rank == 0 or ctx.world == 1:          # (RANK=1 WORLD_SIZE=1 reruns another rank's shard on one GPU)
             _emit(line)
         ctx.finish()
         return
     line, cpu = run_vectorize(ctx, args, args.steps, args.warmup)
     if want_cpu:
-        line["cpu_baseline"] = cpu(cpu_sample)
+        line["cpu_baseline"] = ctx.run_cpu(cpu, cpu_sample)
     del cpu
     ctx.free()
     line["workloads"] = {}
@@ -1122,7 +1140,7 @@ def main():
         try:
             rec, cpu = RUNNERS[name](ctx, args, sub_steps, 3)
             if want_cpu and cpu is not None:
-                rec["cpu_baseline"] = cpu(cpu_sample if name != "learn" else cpu_sample // 2)
+                rec["cpu_baseline"] = ctx.run_cpu(cpu, cpu_sample if name != "learn" else cpu_sample // 2)
             rec["wall_s"] = round(time.time() - t0, 1)
             del cpu
         except Exception as e:          # noqa: BLE001 — the headline line must still be printed; the failure is in the record
