@@ -21,8 +21,9 @@ struct PushArgs {
     int64_t cut[PEER_MAX_WORLD + 1];    // entries [cut[r], cut[r+1]) of the local sorted list belong to rank r
 };
 
-// blockIdx.y = destination rank, so a CTA streams one contiguous run to one peer: two coalesced 8-byte loads and one
-// coalesced 8-byte store per entry (a warp's store is 256 contiguous bytes on the NVLink).
+// blockIdx.y = destination rank, so a CTA streams one contiguous run to one peer.  The stores are 16 bytes per thread (two
+// entries; a warp's store instruction is 512 contiguous bytes on the NVLink) once the destination is 16-byte aligned;
+// the loads are local.
 __global__ void __launch_bounds__(256) coo_pack_push_kernel(const uint64_t *__restrict__ keys, const int64_t *__restrict__ vals,
                                                             const PushArgs a, int world, int count_bits, int *__restrict__ overflow) {
     const uint64_t vmax = 1ull << count_bits, kmax = 1ull << (64 - count_bits);
@@ -32,11 +33,23 @@ __global__ void __launch_bounds__(256) coo_pack_push_kernel(const uint64_t *__re
     uint64_t *__restrict__ out = a.dst[r] + a.dst_off[r];
     const uint64_t *__restrict__ k = keys + lo;
     const int64_t *__restrict__ v = vals + lo;
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    auto pack = [&](int64_t i) {
         const uint64_t kk = k[i], vv = uint64_t(v[i]);
         bad |= (vv >= vmax) | (kk >= kmax);
-        out[i] = (kk << count_bits) | (vv & (vmax - 1));
+        return (kk << count_bits) | (vv & (vmax - 1));
+    };
+    const int64_t head = (n > 0 && (reinterpret_cast<uintptr_t>(out) & 8)) ? 1 : 0;      // entries in front of the first aligned pair
+    const int64_t pairs = (n - head) >> 1;
+    const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, stride = int64_t(gridDim.x) * blockDim.x;
+    if (tid == 0 && head) out[0] = pack(0);
+    if (tid == 1 && ((n - head) & 1)) out[n - 1] = pack(n - 1);
+    ulonglong2 *__restrict__ out2 = reinterpret_cast<ulonglong2 *>(out + head);
+    for (int64_t p = tid; p < pairs; p += stride) {
+        const int64_t i = head + 2 * p;
+        ulonglong2 w;
+        w.x = pack(i);
+        w.y = pack(i + 1);
+        out2[p] = w;
     }
     if (bad) atomicOr(overflow, 1);
 }
@@ -104,7 +117,7 @@ int skm_coo_pack_push(const uint64_t *d_keys, const int64_t *d_vals, const int64
     if (longest == 0) return SKM_OK;
     if (!d_keys || !d_vals) { set_error("skm_coo_pack_push: NULL argument"); return SKM_ERR_INVALID; }
     // enough CTAs in flight per destination to cover the NVLink round trip; the grid's y dimension is the destination
-    const int per_dst = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, sm_count() * 8 / world));
+    const int per_dst = (int)std::min<int64_t>((longest / 2 + 255) / 256 + 1, std::max(1, sm_count() * 8 / world));
     coo_pack_push_kernel<<<dim3(per_dst, world), 256, 0, st>>>(d_keys, d_vals, a, world, count_bits, d_overflow);
     SKM_LAUNCH_CHECK("coo_pack_push_kernel");
     return SKM_OK;
