@@ -172,6 +172,19 @@ constexpr int SPA_EB = 512;        // query entries staged per block (one per th
 static_assert(SPA_EB <= SPA_THREADS, "the staging step gives every staged query entry its own thread");
 constexpr int SPA_SEG = 512;       // CSC entries per segment (16 per lane)
 
+// acc[w >> 16] += c * (w & 0xFFFF): one red.shared.add on the 32-bit shared address `acc` (address of accumulator 0),
+// no predicate and no branch — a lane without an entry adds 0 to a dummy accumulator of its own behind the real ones.
+template <typename AccT> __device__ __forceinline__ void spa_red_add(uint32_t acc, uint32_t w, uint32_t c);
+template <> __device__ __forceinline__ void spa_red_add<uint32_t>(uint32_t acc, uint32_t w, uint32_t c) {
+    const uint32_t a = acc + ((w >> 16) << 2);
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(c * (w & 0xFFFFu)) : "memory");
+}
+template <> __device__ __forceinline__ void spa_red_add<unsigned long long>(uint32_t acc, uint32_t w, uint32_t c) {
+    const uint32_t a = acc + ((w >> 16) << 3);
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"((unsigned long long)c * (w & 0xFFFFu)) : "memory");
+}
+constexpr int SPA_DUMMY = 32;      // dummy accumulators behind the padded real ones: one per lane
+
 // One CTA per query (grid-stride).  acc: one integer per annotation in shared memory (AccT = uint32 when every dot
 // fits 32 bits — the host checks max(M) * max row total < 2^32 — else uint64).
 //   walk   the query's (k-mer, count) entries are staged in shared memory with their column ranges; the warps share
@@ -196,11 +209,13 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
     __shared__ int s_first[SPA_EB + 1];                 // segments of the block's entries before entry j (exclusive prefix)
     __shared__ int s_wtot[SPA_THREADS / 32];
     AccT *acc = reinterpret_cast<AccT *>(s_raw);
+    const uint32_t acc_addr = smem_addr(acc);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = SPA_THREADS / 32;
     constexpr int PER = 16 / sizeof(AccT);                 // accumulators per 16-byte step of the scan
     const int n_pad = (n_ann + PER - 1) / PER * PER;
-    for (int i = tid; i < n_pad; i += SPA_THREADS) acc[i] = 0;
+    const uint32_t pad_word = uint32_t(n_pad + lane) << 16;          // packed path: (dummy accumulator of this lane, value 0)
+    for (int i = tid; i < n_pad + SPA_DUMMY; i += SPA_THREADS) acc[i] = 0;
     if (tid == 0) s_n2 = 0;
     __syncthreads();
     for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
@@ -257,27 +272,36 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
                     // one 32-bit word per CSC entry (annotation << 16 | value): half the loads and registers, which pays
                     // for a software pipeline — the next item's 8 loads are issued before the current item's atomics
                     // (22 % of the samples of the unpacked kernel wait on the loads of the item they are about to use)
-                    uint32_t cur[SPA_SEG / 32], n1[SPA_SEG / 32], n2[SPA_SEG / 32];
+                    uint32_t b0[SPA_SEG / 32], b1[SPA_SEG / 32], b2[SPA_SEG / 32];
                     auto fetch = [&](int i, uint32_t (&dst)[SPA_SEG / 32]) -> uint32_t {
                         const int j = __shfl_sync(FULL, ej, i), seg = __shfl_sync(FULL, es, i);
                         const int64_t pb = s_p0[j] + int64_t(seg) * SPA_SEG;
                         const int n = min(SPA_SEG, s_len[j] - seg * SPA_SEG);
 #pragma unroll
-                        for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; dst[u] = (idx < n) ? __ldg(packed + pb + idx) : 0u; }
+                        for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; dst[u] = (idx < n) ? __ldg(packed + pb + idx) : pad_word; }
                         return s_cnt[j];
                     };
-                    // two items of look-ahead: 16 loads per lane in flight while the current item's atomics run
-                    uint32_t c0 = fetch(0, cur), c1 = 0, c2 = 0;
-                    if (in_round > 1) c1 = fetch(1, n1);
-                    for (int i = 0; i < in_round; ++i) {
-                        if (i + 2 < in_round) c2 = fetch(i + 2, n2);
-                        const AccT cnt = AccT(c0);
+                    // acc[word >> 16] += count * (word & 0xFFFF) as ONE unpredicated red.shared on a 32-bit shared address; a
+                    // lane without an entry holds pad_word = (its dummy accumulator, value 0).  The compiler's version of
+                    // `if (w & 0xFFFF) atomicAdd(...)` was a branch with a reconvergence barrier around every atomic plus the
+                    // recomputation of the shared window base: 11 instructions per entry instead of 5.
+                    auto add_all = [&](const uint32_t (&w)[SPA_SEG / 32], uint32_t c) {
 #pragma unroll
-                        for (int u = 0; u < SPA_SEG / 32; ++u)
-                            if (cur[u] & 0xFFFFu) atomicAdd(&acc[cur[u] >> 16], cnt * AccT(cur[u] & 0xFFFFu));      // values are >= 1
-#pragma unroll
-                        for (int u = 0; u < SPA_SEG / 32; ++u) { cur[u] = n1[u]; n1[u] = n2[u]; }
-                        c0 = c1; c1 = c2;
+                        for (int u = 0; u < SPA_SEG / 32; ++u) spa_red_add<AccT>(acc_addr, w[u], c);
+                    };
+                    // two items of look-ahead (16 loads per lane in flight while the current item's atomics run); the three
+                    // buffers rotate by name, not by register moves
+                    uint32_t c0 = fetch(0, b0), c1 = 0, c2 = 0;
+                    if (in_round > 1) c1 = fetch(1, b1);
+                    for (int i = 0; i < in_round; i += 3) {
+                        if (i + 2 < in_round) c2 = fetch(i + 2, b2);
+                        add_all(b0, c0);
+                        if (i + 1 >= in_round) break;
+                        if (i + 3 < in_round) c0 = fetch(i + 3, b0);
+                        add_all(b1, c1);
+                        if (i + 2 >= in_round) break;
+                        if (i + 4 < in_round) c1 = fetch(i + 4, b1);
+                        add_all(b2, c2);
                     }
                     continue;
                 }
@@ -852,9 +876,9 @@ int skm_apply_sparse(const int64_t *d_rowptr, const uint32_t *d_cols, const int3
     if (nq < 0 || n_ann <= 0 || n_ann > cap) { set_error("skm_apply_sparse: n_ann=%lld outside [1, %lld] for %d-bit accumulators (shard the annotations)", (long long)n_ann, (long long)cap, acc_bits); return n_ann > cap ? SKM_ERR_UNSUPPORTED : SKM_ERR_INVALID; }
     if (nq == 0) return SKM_OK;
     if (!d_rowptr || !d_colptr || !d_mnorm2 || !d_inv_m32 || !d_top1 || !d_top2 || !d_score1 || !d_score2) { set_error("skm_apply_sparse: NULL argument"); return SKM_ERR_INVALID; }
-    if (d_packed && n_ann > 65536) { set_error("skm_apply_sparse: the packed CSC holds 16-bit annotation indices (n_ann <= 65536)"); return SKM_ERR_INVALID; }
+    if (d_packed && n_ann > 65536 - 4 - SPA_DUMMY) { set_error("skm_apply_sparse: the packed CSC holds 16-bit annotation indices (n_ann <= 65500)"); return SKM_ERR_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_inv_m32) & 15u) != 0) { set_error("skm_apply_sparse: d_inv_m32 must be 16-byte aligned (vector loads)"); return SKM_ERR_INVALID; }
-    const size_t smem = std::max<size_t>(size_t(n_ann + 4) * (acc_bits / 8), 116 * 1024);   // > half an SM: one CTA per SM by construction
+    const size_t smem = std::max<size_t>(size_t(n_ann + 4 + SPA_DUMMY) * (acc_bits / 8), 116 * 1024);   // > half an SM: one CTA per SM by construction
     const int grid = (int)std::min<int64_t>(nq, int64_t(sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
 #define SKM_LAUNCH_SPA(ACC, PK)                                                                                              \

@@ -481,3 +481,24 @@ def test_learn_sparse_onchip_degenerate_inputs():
     empty = E.SequenceBatch.from_strings([])
     k0, v0, t0 = E.learn_sparse_onchip(empty, "syn6", 8, torch.zeros(0, dtype=torch.int32), 6, want_totals=True)
     assert k0.numel() == 0 and v0.numel() == 0 and int(t0.sum().item()) == 0
+
+
+@pytest.mark.parametrize("a,k,n", [("miqs", 3, 3000), ("miqs", 3, 12), (2, 4, 400), ("hydro", 10, 2000), (0, 3, 40)])
+def test_vectorize_order_only_overlapped_readback(a, k, n):
+    """vectorize_order_only (count pass launched over S columns before K is read back) == basis + counts of the two
+    separate calls and of the oracle, for saturated spaces (K = S) and unsaturated ones (K < S: compacted)."""
+    rng = np.random.default_rng(n + k)
+    seqs = _rand_seqs(rng, n, 0, 120)
+    batch = E.SequenceBatch.from_strings(seqs)
+    basis, counts = E.vectorize_order_only(batch, a, k)
+    ref = E.build_basis(batch, a, k, 0, counts=False)
+    want_codes, _, (si, code, valid) = _oracle_basis(seqs, a, k)
+    assert basis.K == ref.K == len(want_codes)
+    assert np.array_equal(basis.codes_host(), want_codes) and torch.equal(basis.col_of_code, ref.col_of_code)
+    assert tuple(counts.shape) == (n, basis.K) and counts.is_contiguous()
+    assert torch.equal(counts, E.count_dense(batch, a, k, ref))
+    assert np.array_equal(counts.cpu().numpy(), O.count_matrix(si, code, valid, n, want_codes))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    out = torch.empty((n, basis.S), dtype=torch.int32, device="cuda")
+    b2, c2 = E.vectorize_order_only(batch, a, k, out=out, count_events=ev)
+    assert torch.equal(c2, counts) and (c2.data_ptr() == out.data_ptr()) == (basis.K == basis.S)
