@@ -325,8 +325,58 @@ def build_basis(batch: SequenceBatch, alphabet: AlphabetT, k: int, min_filter: i
     return basis_finalize(alphabet, k, count, first, min_filter)
 
 
+class OrderOnlyPlan:
+    """The launch-bound front of the vectorize rule for ONE resident batch — table reset, order-only basis walk
+    (4 chunk launches), key build, sort and emit of the finalisation: ten tiny kernels, ~0.15 ms of host-paced launches in
+    front of a 0.85 ms count pass — captured once into a CUDA graph and replayed as a single launch.  The graph holds
+    the batch's pointers and chunk geometry, so a plan belongs to its batch (a resident upload buffer that is refilled
+    with batches of the same layout keeps its plan only if the offsets are the same; otherwise build a new one or run
+    without).  Capture failure (a driver that refuses a node) leaves `graph = None`: the calls then run eagerly."""
+
+    def __init__(self, batch: SequenceBatch, alphabet: AlphabetT, k: int, capture: bool = True):
+        tab = alphabet_tables(alphabet, batch.device)
+        dev = batch.device
+        S = code_space(tab.nsym, k)
+        if not order_only_supported(S):
+            raise SkmError(-3, f"OrderOnlyPlan: code space {tab.nsym}^{k} exceeds {lib().skm_basis_order_max_space()}")
+        self.batch, self.alphabet, self.k, self.tab, self.S = batch, alphabet, int(k), tab, S
+        self.first = torch.empty(S, dtype=torch.int64, device=dev)
+        self.state = torch.empty(4, dtype=torch.int32, device=dev)
+        self.ws_bytes = lib().skm_basis_finalize_workspace(S)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.codes = torch.empty(S, dtype=torch.int64, device=dev)
+        self.col = torch.empty(S, dtype=torch.int32, device=dev)
+        self.dK = torch.empty(1, dtype=torch.int64, device=dev)
+        self.graph = None
+        if capture:
+            self.enqueue()                               # eager once: function attributes, lazy module loading
+            torch.cuda.synchronize(dev)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.enqueue()
+                self.graph = g
+            except Exception:                            # noqa: BLE001 — stay on the eager path
+                self.graph = None
+                torch.cuda.synchronize(dev)
+
+    def enqueue(self) -> None:
+        self.first.fill_(-1)
+        self.state.zero_()
+        self.dK.zero_()
+        basis_first_progressive(self.batch, self.alphabet, self.k, self.first, self.state, 0)
+        check(lib().skm_basis_finalize(None, _ptr(self.first), self.S, 0, _ptr(self.codes), None, _ptr(self.col), _ptr(self.dK),
+                                       _ptr(self.ws), self.ws_bytes, _stream()))
+
+    def launch(self) -> None:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.enqueue()
+
+
 def vectorize_order_only(batch: SequenceBatch, alphabet: AlphabetT, k: int, out: Optional[torch.Tensor] = None,
-                         dtype: torch.dtype = torch.int32, count_events=None) -> Tuple[Basis, torch.Tensor]:
+                         dtype: torch.dtype = torch.int32, count_events=None, plan: Optional[OrderOnlyPlan] = None) -> Tuple[Basis, torch.Tensor]:
     """Both passes of the vectorize rule (kmerize.smk:89-120) for min_filter = 0 over a small code space
     (order_only_supported): order-only basis walk + dense counts, with the read-back of K taken OFF the critical path.
     K only sizes the output, and K <= S: the count pass is launched with S columns (the column map sends every basis
@@ -334,21 +384,17 @@ def vectorize_order_only(batch: SequenceBatch, alphabet: AlphabetT, k: int, out:
     latency around it overlap the count kernel instead of leaving the GPU idle between the passes (~0.07 ms of a
     1.04 ms C2 step).  Returns (basis, counts [N, K]); when the space is not saturated (K < S) the counts are compacted
     to K columns.  `out`: optional [N, S] buffer; `count_events`: optional (start, end) CUDA events recorded around the
-    count launch."""
+    count launch; `plan`: an OrderOnlyPlan of THIS batch (the front of the step as one CUDA-graph launch).  The basis
+    tensors of the result alias the plan's buffers: they are valid until the plan is launched again."""
     tab = alphabet_tables(alphabet, batch.device)
     dev = batch.device
     S = code_space(tab.nsym, k)
-    if not order_only_supported(S):
-        raise SkmError(-3, f"vectorize_order_only: code space {tab.nsym}^{k} exceeds {lib().skm_basis_order_max_space()}")
-    first = torch.full((S,), -1, dtype=torch.int64, device=dev)
-    state = torch.zeros(4, dtype=torch.int32, device=dev)
-    basis_first_progressive(batch, alphabet, k, first, state, 0)
-    ws_bytes = lib().skm_basis_finalize_workspace(S)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    codes = torch.empty(S, dtype=torch.int64, device=dev)
-    col = torch.empty(S, dtype=torch.int32, device=dev)
-    dK = torch.zeros(1, dtype=torch.int64, device=dev)
-    check(lib().skm_basis_finalize(None, _ptr(first), S, 0, _ptr(codes), None, _ptr(col), _ptr(dK), _ptr(ws), ws_bytes, _stream()))
+    if plan is None:
+        plan = OrderOnlyPlan(batch, alphabet, k, capture=False)
+    else:
+        assert plan.batch is batch and plan.S == S and plan.k == int(k) and plan.tab.name == tab.name
+    plan.launch()
+    codes, col, dK = plan.codes, plan.col, plan.dK
     bits = {torch.int32: 32, torch.uint16: 16, torch.int16: 16}[dtype]
     if out is None:
         out = torch.empty((batch.n, S), dtype=dtype, device=dev)

@@ -502,3 +502,9 @@ def test_vectorize_order_only_overlapped_readback(a, k, n):
     out = torch.empty((n, basis.S), dtype=torch.int32, device="cuda")
     b2, c2 = E.vectorize_order_only(batch, a, k, out=out, count_events=ev)
     assert torch.equal(c2, counts) and (c2.data_ptr() == out.data_ptr()) == (basis.K == basis.S)
+    plan = E.OrderOnlyPlan(batch, a, k)                  # the front of the step as one CUDA-graph launch, replayed twice
+    assert plan.graph is not None
+    for _ in range(2):
+        out.fill_(-7)
+        b3, c3 = E.vectorize_order_only(batch, a, k, out=out, plan=plan)
+        assert b3.K == basis.K and torch.equal(b3.codes, basis.codes) and torch.equal(c3, counts)
