@@ -285,7 +285,7 @@ SKM_API int skm_csc_build(const uint64_t *d_keys, const int64_t *d_vals, int64_t
  * dot * (1/||q||) * (1/||m||) in float64 like skm_apply_dense, ties -> lowest index.
  * n_ann <= 51200 (32-bit) or 25600 (64-bit) per call: shard the annotations and merge with
  * skm_top2_merge.  d_qnorm2 (nullable) receives ||q||^2.  d_inv_m32 must be 16-byte aligned.
- * d_packed (nullable): the CSC entries as one 32-bit word each, annotation << 16 | value (skm_csc_pack; needs
+ * d_packed (nullable): the CSC entries as one 32-bit word each, value << 16 | annotation (skm_csc_pack; needs
  * n_ann <= 65536 and every value < 65536) — the kernel then reads half the bytes and pipelines its loads;
  * d_rows / d_mvals are not read in that case. */
 SKM_API int skm_csc_pack(const int32_t *d_rows, const int32_t *d_mvals, int64_t nnz, uint32_t *d_packed,

@@ -172,16 +172,20 @@ constexpr int SPA_EB = 512;        // query entries staged per block (one per th
 static_assert(SPA_EB <= SPA_THREADS, "the staging step gives every staged query entry its own thread");
 constexpr int SPA_SEG = 512;       // CSC entries per segment (16 per lane)
 
-// acc[w >> 16] += c * (w & 0xFFFF): one red.shared.add on the 32-bit shared address `acc` (address of accumulator 0),
+// acc[w & 0xFFFF] += c * (w >> 16): one red.shared.add on the 32-bit shared address `acc` (address of accumulator 0),
 // no predicate and no branch — a lane without an entry adds 0 to a dummy accumulator of its own behind the real ones.
+// Annotation in the LOW half: the address is one mask + one scaled add, the value one shift (5 instructions per entry
+// with the multiply and the red).
 template <typename AccT> __device__ __forceinline__ void spa_red_add(uint32_t acc, uint32_t w, uint32_t c);
 template <> __device__ __forceinline__ void spa_red_add<uint32_t>(uint32_t acc, uint32_t w, uint32_t c) {
-    const uint32_t a = acc + ((w >> 16) << 2);
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(c * (w & 0xFFFFu)) : "memory");
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(w & 0xFFFFu), "r"(acc));       // one mask + one multiply-add
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(c * (w >> 16)) : "memory");
 }
 template <> __device__ __forceinline__ void spa_red_add<unsigned long long>(uint32_t acc, uint32_t w, uint32_t c) {
-    const uint32_t a = acc + ((w >> 16) << 3);
-    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"((unsigned long long)c * (w & 0xFFFFu)) : "memory");
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a) : "r"(w & 0xFFFFu), "r"(acc));
+    asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(a), "l"((unsigned long long)c * (w >> 16)) : "memory");
 }
 constexpr int SPA_DUMMY = 32;      // dummy accumulators behind the padded real ones: one per lane
 
@@ -214,7 +218,7 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
     constexpr int NW = SPA_THREADS / 32;
     constexpr int PER = 16 / sizeof(AccT);                 // accumulators per 16-byte step of the scan
     const int n_pad = (n_ann + PER - 1) / PER * PER;
-    const uint32_t pad_word = uint32_t(n_pad + lane) << 16;          // packed path: (dummy accumulator of this lane, value 0)
+    const uint32_t pad_word = uint32_t(n_pad + lane);                // packed path: (value 0, dummy accumulator of this lane)
     for (int i = tid; i < n_pad + SPA_DUMMY; i += SPA_THREADS) acc[i] = 0;
     if (tid == 0) s_n2 = 0;
     __syncthreads();
@@ -281,7 +285,7 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
                         for (int u = 0; u < SPA_SEG / 32; ++u) { const int idx = lane + 32 * u; dst[u] = (idx < n) ? __ldg(packed + pb + idx) : pad_word; }
                         return s_cnt[j];
                     };
-                    // acc[word >> 16] += count * (word & 0xFFFF) as ONE unpredicated red.shared on a 32-bit shared address; a
+                    // acc[word & 0xFFFF] += count * (word >> 16) as ONE unpredicated red.shared on a 32-bit shared address; a
                     // lane without an entry holds pad_word = (its dummy accumulator, value 0).  The compiler's version of
                     // `if (w & 0xFFFF) atomicAdd(...)` was a branch with a reconvergence barrier around every atomic plus the
                     // recomputation of the shared window base: 11 instructions per entry instead of 5.
@@ -354,12 +358,19 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
             for (int i = 0; i < PER; ++i) any |= (v[i] != 0);
             if (any) {
                 *reinterpret_cast<uint4 *>(&acc[a0]) = make_uint4(0u, 0u, 0u, 0u);
+                // group screening: ONE comparison of the group's largest float32 score against the threshold; the
+                // per-accumulator path (insertion into the running top-2) runs only for a group that holds a candidate.
+                // A zero dot gives 0 < thr, so zero dots are never candidates.  (One branchy copy of the insertion per
+                // accumulator made the scan 25 % of the kernel's instructions.)
+                float f[PER];
+                float fm = 0.f;
 #pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    if (v[i] != 0) {
-                        const float f = float(v[i]) * inv[i];
-                        if (f >= thr) {
-                            top2x_push(bx, f, (unsigned long long)v[i], a0 + i, inv_qn, mnorm2);
+                for (int i = 0; i < PER; ++i) { f[i] = float(v[i]) * inv[i]; fm = fmaxf(fm, f[i]); }
+                if (fm >= thr) {
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        if (f[i] >= thr) {
+                            top2x_push(bx, f[i], (unsigned long long)v[i], a0 + i, inv_qn, mnorm2);
                             if (bx.i2 >= 0) thr = fmaxf(thr, bx.f2 * 0.99999f);
                         }
                     }
@@ -395,7 +406,7 @@ apply_sparse_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restri
 __global__ void __launch_bounds__(256) csc_pack_kernel(const int32_t *__restrict__ rows, const int32_t *__restrict__ mvals, int64_t nnz,
                                                        uint32_t *__restrict__ packed) {
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nnz; i += int64_t(gridDim.x) * blockDim.x)
-        packed[i] = (uint32_t(rows[i]) << 16) | (uint32_t(mvals[i]) & 0xFFFFu);
+        packed[i] = (uint32_t(mvals[i]) << 16) | (uint32_t(rows[i]) & 0xFFFFu);      // value high, annotation low
 }
 
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }

@@ -1269,12 +1269,12 @@ class AnnotationCSC:
     n_ann: int
     ann_lo: int
     S: int
-    packed: Optional[torch.Tensor] = None   # int32 (uint32 pattern) [nnz]: row << 16 | value, when n_ann <= 65536 and max_m < 65536
+    packed: Optional[torch.Tensor] = None   # int32 (uint32 pattern) [nnz]: value << 16 | row, when n_ann <= 65536 and max_m < 65536
 
 
 def csc_build(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int, ann_lo: int = 0, pack: bool = True) -> AnnotationCSC:
     """CSC of the annotation slice [ann_lo, ann_lo + n_ann) of a sorted COO matrix.  pack: also keep the entries as one
-    32-bit word each (annotation << 16 | value) when they fit — apply_sparse then reads half the bytes."""
+    32-bit word each (value << 16 | annotation) when they fit — apply_sparse then reads half the bytes."""
     dev = _require_cuda(keys.device)
     if keys.numel():
         # the slice is contiguous because the list is sorted by ann * S + code

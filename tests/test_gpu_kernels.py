@@ -446,7 +446,7 @@ def test_learn_sparse_with_totals(a, k):
 
 @pytest.mark.parametrize("a,k", [(2, 6), (5, 3), (1, 4)])
 def test_apply_sparse_packed_csc_identical(a, k):
-    """The 4-byte packed CSC (annotation << 16 | value, pipelined loads) gives bit-identical results to the 8-byte one,
+    """The 4-byte packed CSC (value << 16 | annotation, pipelined loads) gives bit-identical results to the 8-byte one,
     and csc_build refuses to pack entries that do not fit 16 bits."""
     rng = np.random.default_rng(k + 300)
     train = _rand_seqs(rng, 1500, 20, 300)
