@@ -613,19 +613,15 @@ def run_learn(ctx, args, steps, warmup):
     e2e_ms = 0.0
     nnz = int(state["keys"].numel())
     if not args.no_e2e:
+        from snekmer_b200 import pipeline as P
         h_res = torch.empty(nres, dtype=torch.uint8, pin_memory=True); h_res.numpy()[:] = res_np
         h_ann = torch.from_numpy(ann).pin_memory()
         cap = int(state["local_nnz"]) + 1024
-        h_k = torch.empty(cap, dtype=torch.int64, pin_memory=True)
-        h_v = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+        h_w = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+        box = {}
 
         def once():
-            b = E.SequenceBatch.from_packed(h_res.numpy(), offsets, ctx.dev, pinned=True)
-            kk, vv = E.learn_sparse(b, alphabet, k, h_ann.to(ctx.dev, non_blocking=True), n_ann)
-            m = kk.numel()
-            h_k[:m].copy_(kk, non_blocking=True)
-            h_v[:m].copy_(vv, non_blocking=True)
-            torch.cuda.synchronize()
+            box["r"] = P.learn_host(h_res, offsets, h_ann, alphabet, k, n_ann, out=h_w, device=ctx.dev)
         e2e_ms = _e2e_time(ctx, once, 2)
     total_ms, c_ms = ctx.max_over_ranks([total_ms, float(np.mean(comm_ms)) if comm_ms else 0.0])
     ms = total_ms / steps
@@ -656,8 +652,10 @@ def run_learn(ctx, args, steps, warmup):
                         "traffic": None, "note": "local part of the step; B_learn of SURVEY 8(d)"}}
     if not args.no_e2e:
         rec["e2e"] = {"value": ctx.world * nseq / (e2e_ms * 1e-3), "unit": "sequences/s", "ms_per_step": e2e_ms,
-                      "h2d_bytes_per_step": nres + 8 * (batch.n + 1) + 4 * batch.n, "d2h_bytes_per_step": 16 * local_nnz,
-                      "api": "engine.SequenceBatch.from_packed(pinned host) + engine.learn_sparse -> pinned host COO (wall clock)"}
+                      "h2d_bytes_per_step": nres + 8 * (batch.n + 1) + 4 * batch.n,
+                      "d2h_bytes_per_step": (8 if box["r"].packed is not None else 16) * box["r"].nnz,
+                      "api": "snekmer_b200.pipeline.learn_host: pinned host residues + annotation ids -> pinned host COO in the packed "
+                             "exchange format (key << count_bits | count, 8 B per entry; HostCOO.keys() / vals() unpack); wall clock"}
 
     def cpu(sample):
         from oracle import cpu_baseline

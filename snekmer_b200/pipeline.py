@@ -284,3 +284,53 @@ def apply_host(residues: torch.Tensor, offsets: np.ndarray, alphabet, k: int, pr
     main.wait_stream(s_out)
     torch.cuda.current_stream(dev).synchronize()
     return HostScores(out[0].numpy(), out[1].numpy(), out[2].numpy(), out[3].numpy())
+
+
+@dataclass
+class HostCOO:
+    """learn_host result in host memory: the annotation x k-mer count matrix as a COO list sorted by key = ann * S + code.
+    `packed` (uint64 [nnz], key << count_bits | count) is what crossed PCIe — 8 bytes per entry; keys() / vals() unpack."""
+    S: int
+    n_ann: int
+    count_bits: int
+    packed: Optional[np.ndarray] = None     # uint64 [nnz]
+    raw: Optional[Tuple[np.ndarray, np.ndarray]] = None     # (keys int64, vals int64) when a count did not fit count_bits
+
+    @property
+    def nnz(self) -> int:
+        return int(self.packed.size if self.packed is not None else self.raw[0].size)
+
+    def keys(self) -> np.ndarray:
+        return (self.packed >> np.uint64(self.count_bits)).astype(np.int64) if self.packed is not None else self.raw[0]
+
+    def vals(self) -> np.ndarray:
+        if self.packed is None:
+            return self.raw[1]
+        return (self.packed & np.uint64((1 << self.count_bits) - 1)).astype(np.int64)
+
+
+def learn_host(residues: torch.Tensor, offsets: np.ndarray, ann_id, alphabet, k: int, n_ann: int,
+               out: Optional[torch.Tensor] = None, device=None) -> HostCOO:
+    """Host residues + annotation ids -> the learned count matrix in host memory (learn.smk:306-326, 385-408 for one
+    shard).  The matrix is built on the device (engine.learn_sparse_hybrid) and comes back in the packed exchange format
+    of the multi-GPU fan-in (skm_coo_pack: 8 bytes per entry instead of 16).  `out`: optional pinned int64 tensor with
+    room for the entries (at most one per residue)."""
+    dev = E._require_cuda(device)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    batch = E.SequenceBatch.from_packed(residues.numpy() if isinstance(residues, torch.Tensor) else residues, offsets, dev,
+                                        pinned=isinstance(residues, torch.Tensor) and residues.is_pinned())
+    ann = ann_id if isinstance(ann_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ann_id, dtype=np.int32))
+    keys, vals = E.learn_sparse_hybrid(batch, alphabet, k, ann.to(dev, non_blocking=True), n_ann)
+    S = E.code_space(E.alphabet_tables(alphabet, dev).nsym, k)
+    count_bits = 64 - max(int(n_ann) * int(S) - 1, 1).bit_length()
+    m = int(keys.numel())
+    if count_bits >= 16:
+        packed, bad = E.coo_pack(keys, vals, count_bits)
+        if not bad:
+            if out is None or out.numel() < m:
+                out = torch.empty(max(m, 1), dtype=torch.int64, pin_memory=True)
+            out[:m].copy_(packed, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return HostCOO(S, int(n_ann), count_bits, packed=out[:m].numpy().view(np.uint64))
+    hk, hv = keys.cpu().numpy(), vals.cpu().numpy()
+    return HostCOO(S, int(n_ann), count_bits, raw=(hk, hv))

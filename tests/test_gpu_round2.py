@@ -508,3 +508,25 @@ def test_vectorize_order_only_overlapped_readback(a, k, n):
         out.fill_(-7)
         b3, c3 = E.vectorize_order_only(batch, a, k, out=out, plan=plan)
         assert b3.K == basis.K and torch.equal(b3.codes, basis.codes) and torch.equal(c3, counts)
+
+
+def test_learn_host_packed_download_equals_device_path(monkeypatch):
+    """pipeline.learn_host: host residues + annotation ids -> host COO in the packed 8-byte format == the device lists of
+    learn_sparse; a count beyond the packed word's count bits comes back unpacked."""
+    from snekmer_b200 import pipeline as P
+
+    rng = np.random.default_rng(21)
+    seqs = _rand_seqs(rng, 1500, 0, 200)
+    ann = rng.integers(-1, 30, size=len(seqs)).astype(np.int32)
+    res, offs = O.pack(seqs)
+    batch = E.SequenceBatch.from_strings(seqs)
+    k1, v1 = E.learn_sparse(batch, 2, 8, torch.from_numpy(ann), 30)
+    h = P.learn_host(torch.from_numpy(res).pin_memory(), offs, ann, 2, 8, 30)
+    assert h.packed is not None and h.nnz == k1.numel()
+    assert np.array_equal(h.keys(), k1.cpu().numpy()) and np.array_equal(h.vals(), v1.cpu().numpy())
+    out = torch.empty(h.nnz + 5, dtype=torch.int64, pin_memory=True)
+    h2 = P.learn_host(torch.from_numpy(res), offs, torch.from_numpy(ann), 2, 8, 30, out=out)
+    assert np.array_equal(h2.keys(), h.keys()) and np.array_equal(h2.vals(), h.vals())
+    monkeypatch.setattr(E, "coo_pack", lambda keys, vals, bits: (None, True))       # a count that does not fit: unpacked download
+    h3 = P.learn_host(torch.from_numpy(res), offs, ann, 2, 8, 30)
+    assert h3.packed is None and np.array_equal(h3.keys(), k1.cpu().numpy()) and np.array_equal(h3.vals(), v1.cpu().numpy())
