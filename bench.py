@@ -222,6 +222,8 @@ class Ctx:
         """warm-up, then EXACTLY `steps` steps between barrier+sync pairs; returns total ms (this rank) and clocks."""
         torch = self.torch
         # rank 0 samples the GPUs of ALL ranks (median clock over all samples, union of the throttle reasons)
+        if os.environ.get("SKM_NO_CLOCKS"):            # experiment: is the sampler what perturbs 1-ms steps at 8 ranks?
+            clocks = False
         sampler = ClockSampler(",".join(str(i) for i in range(self.world))) if clocks and self.rank == 0 else None
         if sampler:
             sampler.start()                  # nvidia-smi needs ~100 ms per sample: it runs from the warm-up on
@@ -1093,8 +1095,8 @@ def main():
     _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="all", choices=["all"] + sorted(RUNNERS),
                     help="all (default) = the headline C2 vectorize line + the apply / learn / apply_sparse / c1 sub-records under "
