@@ -542,14 +542,16 @@ def run_learn(ctx, args, steps, warmup):
             done = False
             if E.peer_exchange_enabled(keys):
                 # fused pack + all_to_all: one kernel stores the packed entries into the owners' buffers over NVLink
-                ptr, runs, flag = D.push_coo_by_key_range(keys, vals, kb, count_bits)
-                if timed:
-                    pev[2].record()
-                k3, v3, dn = E.coo_merge_runs_packed(ptr, runs, count_bits, ctx.dev)
-                m, bad = torch.cat([dn, flag.to(torch.int64)]).tolist()
-                if not bad:
-                    keys, vals, done = k3[:m], v3[:m], True
-                del k3, v3
+                pushed = D.push_coo_by_key_range(keys, vals, kb, count_bits)
+                if pushed is not None:
+                    ptr, runs, flag = pushed
+                    if timed:
+                        pev[2].record()
+                    k3, v3, dn = E.coo_merge_runs_packed(ptr, runs, count_bits, ctx.dev)
+                    m, bad = torch.cat([dn, flag.to(torch.int64)]).tolist()
+                    if not bad:
+                        keys, vals, done = k3[:m], v3[:m], True
+                    del k3, v3
             if not done:
                 k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, kb, return_runs=True)
                 if timed:

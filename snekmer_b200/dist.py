@@ -221,31 +221,59 @@ class PeerBuffers:
         self.words = 0
         self.own = None                  # int: device pointer of this rank's buffer
         self.ptrs: List[Optional[int]] = []
+        self.disabled = False            # set (on every rank) when a buffer could not be allocated or mapped
 
-    def ensure(self, words: int) -> None:
-        """Collective: every rank passes the SAME `words` (push_plan's third value)."""
+    def ensure(self, words: int) -> bool:
+        """Collective: every rank passes the SAME `words` (push_plan's third value).  Returns False — on every rank — when
+        any rank could not allocate or map a buffer (no peer access between the GPUs, CUDA IPC closed off by the
+        container): the buffers are then released, `disabled` is set and the callers use the NCCL exchange."""
         import ctypes as C
 
-        from ._native import check, lib
+        from ._native import SkmError, check, lib
+        if self.disabled:
+            return False
         if words <= self.words:
-            return
+            return True
         rank, w = world()
         self.release()
         words = max(int(words * 1.25), 1 << 16)
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        check(lib().skm_peer_alloc(words * 8, C.byref(own), handle))
+        ok = not os.environ.get("SKM_PEER_FAIL")          # test hook: behave as if the allocation had failed
+        if ok:
+            try:
+                check(lib().skm_peer_alloc(words * 8, C.byref(own), handle))
+            except SkmError:
+                ok = False
         handles = [None] * w
-        dist.all_gather_object(handles, bytes(handle))
-        self.ptrs = []
-        for r in range(w):
-            if r == rank:
-                self.ptrs.append(own.value)
-                continue
-            q = C.c_void_p()
-            check(lib().skm_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(q)))
-            self.ptrs.append(q.value)
-        self.own, self.words = own.value, words
+        dist.all_gather_object(handles, (bytes(handle), ok))
+        opened: List[Optional[int]] = []
+        ok = all(h[1] for h in handles)
+        if ok:
+            for r in range(w):
+                if r == rank:
+                    opened.append(own.value)
+                    continue
+                q = C.c_void_p()
+                try:
+                    check(lib().skm_peer_open((C.c_ubyte * 64).from_buffer_copy(handles[r][0]), C.byref(q)))
+                except SkmError:
+                    ok = False
+                    break
+                opened.append(q.value)
+        flags = [None] * w
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            for r, q in enumerate(opened):
+                if r != rank and q:
+                    lib().skm_peer_close(q)
+            dist.barrier()
+            if own.value:
+                lib().skm_peer_free(own.value)
+            self.disabled = True
+            return False
+        self.ptrs, self.own, self.words = opened, own.value, words
+        return True
 
     def release(self) -> None:
         from ._native import lib
@@ -279,7 +307,8 @@ def push_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Se
     tensor, non-zero when any rank saw a key / count that does not fit the packed word — the buffer content is then
     unusable and the caller falls back to alltoall_coo_by_key_range).  The all_reduce of the flag is also the fence that
     says every rank's stores have landed; the CALLER provides the fence before this call (any collective issued after
-    the previous step's last read of the buffer — balanced_annotation_bounds does)."""
+    the previous step's last read of the buffer — balanced_annotation_bounds does).  Returns None (on every rank) when the
+    peer buffers cannot be set up; the caller then exchanges through alltoall_coo_by_key_range."""
     import ctypes as C
 
     from ._native import check, lib
@@ -294,7 +323,8 @@ def push_coo_by_key_range(keys: torch.Tensor, vals: torch.Tensor, key_bounds: Se
     mat_h, cut_h = host[:w * w].reshape(w, w), np.ascontiguousarray(host[w * w:])
     dst_off, runs, words = push_plan(mat_h, rank)
     pb = peer_buffers()
-    pb.ensure(words)
+    if not pb.ensure(words):
+        return None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     ptrs = (C.c_void_p * w)(*pb.ptrs)
     dst_off = np.ascontiguousarray(dst_off)

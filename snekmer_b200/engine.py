@@ -1649,8 +1649,9 @@ def peer_exchange_enabled(t: torch.Tensor) -> bool:
     """The sparse-learn fan-in goes through NVLink peer memory when the ranks are CUDA processes of one node (NCCL
     backend); SKM_EXCHANGE=nccl selects the all_to_all_single baseline."""
     import torch.distributed as dist
+    from . import dist as D
     return (t.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl" and dist.get_world_size() <= 16
-            and os.environ.get("SKM_EXCHANGE", "peer") != "nccl")
+            and os.environ.get("SKM_EXCHANGE", "peer") != "nccl" and not D.peer_buffers().disabled)
 
 
 def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n_ann: int,
@@ -1677,11 +1678,13 @@ def exchange_coo_by_annotation(keys: torch.Tensor, vals: torch.Tensor, S: int, n
         # barrier below) is the fence that says no rank still reads its receive buffer
         if not balance:
             D.barrier()
-        ptr, runs, flag = D.push_coo_by_key_range(keys, vals, key_bounds, count_bits)
-        k3, v3, dn = coo_merge_runs_packed(ptr, runs, count_bits, keys.device)
-        m, bad = torch.cat([dn, flag.to(torch.int64)]).tolist()
-        if not bad:
-            return k3[:m].clone(), v3[:m].clone(), (ann_bounds[rank], ann_bounds[rank + 1])
+        pushed = D.push_coo_by_key_range(keys, vals, key_bounds, count_bits)
+        if pushed is not None:
+            ptr, runs, flag = pushed
+            k3, v3, dn = coo_merge_runs_packed(ptr, runs, count_bits, keys.device)
+            m, bad = torch.cat([dn, flag.to(torch.int64)]).tolist()
+            if not bad:
+                return k3[:m].clone(), v3[:m].clone(), (ann_bounds[rank], ann_bounds[rank + 1])
         # a count beyond count_bits somewhere: the unpacked NCCL exchange below
     k2, v2, runs = D.alltoall_coo_by_key_range(keys, vals, key_bounds, return_runs=True)
     k3, v3 = coo_merge_runs(k2, v2, runs)           # W sorted runs, one per sender: merge tree + reduce-by-key

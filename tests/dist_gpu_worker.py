@@ -87,6 +87,14 @@ def main():
     for _ in range(3):                                    # buffer reuse across steps (fences)
         k4, v4, _ = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)
         assert torch.equal(k4, kb) and torch.equal(v4, vb), "repeated peer exchange"
+    # a node where the peer buffers cannot be set up (no peer access, CUDA IPC closed off): every rank notices in the same
+    # collective, the path is disabled for the process and the NCCL exchange takes over with the same result
+    D.peer_buffers().release()
+    os.environ["SKM_PEER_FAIL"] = "1"
+    k5, v5, _ = E.exchange_coo_by_annotation(keys0, vals0, S, n_ann)
+    del os.environ["SKM_PEER_FAIL"]
+    assert D.peer_buffers().disabled and not E.peer_exchange_enabled(keys0)
+    assert torch.equal(k5, kb) and torch.equal(v5, vb), "fallback when the peer buffers cannot be set up"
     if rank == 0:
         sizes = [sp[2] for sp in spans]
         print("balanced exchange entries per rank:", sizes)
