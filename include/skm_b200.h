@@ -198,6 +198,17 @@ SKM_API int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, cons
                            const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo,
                            int64_t ann_n, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity,
                            int64_t *d_nnz_inout, void *workspace, size_t workspace_bytes, skm_stream_t stream);
+/* skm_learn_sparse_group writing its entries straight into a LARGER sorted list that also holds blocks other paths produce
+ * (the dense rows of heavy annotations, skm_rows_emit): block h belongs to annotation d_ins_ann[h] (ascending) and
+ * d_ins_cum[h] is the inclusive prefix of the block sizes, so an entry of annotation a is stored d_ins_cum[#(ins_ann < a) - 1]
+ * places further up (capacity counts the larger list).  d_ins_pos[h] (pre-set to INT64_MAX by the caller) receives the
+ * smallest index of this list behind block h's predecessors: min over h' >= h, capped by the final *d_nnz_inout, is the
+ * number of this list's entries in front of block h.  d_totals (nullable, int64 [S]) += count per code (learn.smk:380). */
+SKM_API int skm_learn_sparse_group_place(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                                 const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo, int64_t ann_n,
+                                 uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity, int64_t *d_nnz_inout,
+                                 const int64_t *d_ins_ann, const int64_t *d_ins_cum, int64_t n_ins, int64_t *d_ins_pos, int64_t *d_totals,
+                                 void *workspace, size_t workspace_bytes, skm_stream_t stream);
 /* d_out_residues[d_out_offsets[i] ...] = sequence d_sel[i] of (d_residues, d_offsets): reorders / selects
  * sequences on the device (grouping by annotation, learn.smk:316-326 keeps only annotated sequences). */
 SKM_API int skm_gather_sequences(const uint8_t *d_residues, const int64_t *d_offsets, const int64_t *d_sel,

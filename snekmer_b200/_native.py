@@ -66,6 +66,7 @@ SIGNATURES = {
     "skm_count_csr_sorted": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _int, _p, _i64, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "skm_learn_sparse_group_workspace": (_sz, [_i64]),
     "skm_learn_sparse_group": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
+    "skm_learn_sparse_group_place": (_int, [_p, _i64, _p, _i64, _p, _int, _int, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "skm_gather_sequences": (_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "skm_coo_merge_workspace": (_sz, [_i64]),
     "skm_coo_merge": (_int, [_p, _p, _i64, _u64, _p, _p, _p, _p, _sz, _p]),

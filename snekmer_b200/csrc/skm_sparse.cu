@@ -508,19 +508,49 @@ size_t skm_learn_sparse_group_workspace(int64_t nres) {
 }
 
 namespace skm {
-// out[base + i] = (key_base + uniq[i], counts[i]) for the runs below the invalid key; base = *nnz
+// out[base + i (+ shift)] = (key_base + uniq[i], counts[i]) for the runs below the invalid key; base = *nnz (entries this
+// list holds so far).  With a placement (n_ins > 0) the list is written straight into a LARGER sorted list that also holds
+// blocks other paths produce (the dense rows of the heavy annotations, skm_rows_emit): the block of annotation ins_ann[h]
+// (ascending) has ins_cum[h] - ins_cum[h-1] entries, so an entry of annotation a moves up by ins_cum[#(ins_ann < a) - 1];
+// ins_pos[h] (pre-set to INT64_MAX) receives the smallest index of THIS list that lies behind block h's predecessors —
+// the caller's suffix-minimum over h turns it into where block h starts.  totals (nullable): += count per code.
+struct Placement {
+    const int64_t *ins_ann;     // [n_ins] ascending annotation ids of the blocks
+    const int64_t *ins_cum;     // [n_ins] inclusive prefix of the block sizes
+    long long *ins_pos;         // [n_ins]
+    unsigned long long *totals; // [S] or NULL
+    int n_ins;
+};
 __global__ void __launch_bounds__(256) coo_append_kernel(const uint32_t *__restrict__ uniq, const int32_t *__restrict__ counts,
                                                          const int64_t *__restrict__ num_runs, uint32_t invalid, uint64_t key_base,
                                                          const int64_t *__restrict__ nnz, int64_t capacity,
                                                          uint64_t *__restrict__ keys_out, int64_t *__restrict__ vals_out,
-                                                         int64_t *__restrict__ n_new) {
+                                                         int64_t *__restrict__ n_new, uint32_t S, int64_t ann_lo, const Placement pl) {
     int64_t n = *num_runs;
     while (n > 0 && uniq[n - 1] >= invalid) --n;            // at most two trailing runs (invalid key, all-ones fill)
     const int64_t base = *nnz;
-    if (base + n > capacity) n = capacity > base ? capacity - base : 0;      // the host checks the total afterwards
+    if (pl.n_ins == 0 && base + n > capacity) n = capacity > base ? capacity - base : 0;      // the host checks the total afterwards
+    auto blocks_before = [&](int64_t ann) {                 // #(ins_ann < ann)
+        int lo = 0, hi = pl.n_ins;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(pl.ins_ann + mid) < ann) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        keys_out[base + i] = key_base + uniq[i];
-        vals_out[base + i] = counts[i];
+        const uint32_t u = uniq[i];
+        int64_t o = base + i;
+        if (pl.n_ins > 0 || pl.totals) {
+            const uint32_t a_rel = u / S;
+            if (pl.totals) atomicAdd(pl.totals + (u - a_rel * S), (unsigned long long)counts[i]);
+            if (pl.n_ins > 0) {
+                const int hb = blocks_before(ann_lo + a_rel);
+                if (hb > 0) {
+                    // first entry of this slice, or first entry behind a block boundary: a candidate for ins_pos[hb - 1]
+                    if (i == 0 || blocks_before(ann_lo + uniq[i - 1] / S) != hb) atomicMin(pl.ins_pos + (hb - 1), (long long)(base + i));
+                    o += __ldg(pl.ins_cum + hb - 1);
+                }
+            }
+        }
+        if (o < capacity) { keys_out[o] = key_base + u; vals_out[o] = counts[i]; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_new = n;
 }
@@ -531,7 +561,17 @@ int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, const int64_
                            const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo, int64_t ann_n,
                            uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity, int64_t *d_nnz_inout,
                            void *workspace, size_t workspace_bytes, skm_stream_t stream) {
+    return skm_learn_sparse_group_place(d_residues, nres, d_offsets, nseq, d_lut, nsym, k, d_ann_id, ann_lo, ann_n, d_keys_out, d_vals_out,
+                                        out_capacity, d_nnz_inout, nullptr, nullptr, 0, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int skm_learn_sparse_group_place(const uint8_t *d_residues, int64_t nres, const int64_t *d_offsets, int64_t nseq,
+                                 const uint8_t *d_lut, int nsym, int k, const int32_t *d_ann_id, int64_t ann_lo, int64_t ann_n,
+                                 uint64_t *d_keys_out, int64_t *d_vals_out, int64_t out_capacity, int64_t *d_nnz_inout,
+                                 const int64_t *d_ins_ann, const int64_t *d_ins_cum, int64_t n_ins, int64_t *d_ins_pos, int64_t *d_totals,
+                                 void *workspace, size_t workspace_bytes, skm_stream_t stream) {
     using namespace skm;
+    if (n_ins < 0 || n_ins > (1 << 30) || (n_ins > 0 && (!d_ins_ann || !d_ins_cum || !d_ins_pos))) { set_error("skm_learn_sparse_group_place: bad placement"); return SKM_ERR_INVALID; }
     int rc = check_common(d_residues, nres, d_offsets, nseq, d_lut, nsym, k);
     if (rc) return rc;
     if (!ts_supported(nsym, k)) { set_error("skm_learn_sparse_group: nsym=%d k=%d outside the kernel envelope", nsym, k); return SKM_ERR_UNSUPPORTED; }
@@ -574,7 +614,9 @@ int skm_learn_sparse_group(const uint8_t *d_residues, int64_t nres, const int64_
     temp_bytes = temp_cap;
     SKM_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, keys_b, uniq, counts, num_runs, (int)nres, st));
     const int g2 = (int)std::min<int64_t>((nres + 255) / 256, int64_t(sm_count()) * 8);
-    coo_append_kernel<<<g2, 256, 0, st>>>(uniq, counts, num_runs, invalid, uint64_t(ann_lo) * S, d_nnz_inout, out_capacity, d_keys_out, d_vals_out, n_new);
+    const Placement pl{d_ins_ann, d_ins_cum, reinterpret_cast<long long *>(d_ins_pos), reinterpret_cast<unsigned long long *>(d_totals), (int)n_ins};
+    coo_append_kernel<<<g2, 256, 0, st>>>(uniq, counts, num_runs, invalid, uint64_t(ann_lo) * S, d_nnz_inout, out_capacity, d_keys_out, d_vals_out, n_new,
+                                          (uint32_t)S, ann_lo, pl);
     SKM_LAUNCH_CHECK("coo_append_kernel");
     add_i64_kernel<<<1, 1, 0, st>>>(d_nnz_inout, n_new);
     SKM_LAUNCH_CHECK("add_i64_kernel");

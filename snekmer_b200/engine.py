@@ -27,6 +27,8 @@ from . import _native
 from . import alphabet as _alphabet
 from ._native import SkmError, check, lib
 
+INT64_MAX = (1 << 63) - 1
+
 AlphabetT = Union[str, int, None]
 
 
@@ -871,7 +873,7 @@ def coo_pack(keys: torch.Tensor, vals: torch.Tensor, count_bits: int) -> Tuple[t
 
 
 def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n_ann: int,
-                 max_chunk_res: int = 1 << 28, method: str = "grouped") -> Tuple[torch.Tensor, torch.Tensor]:
+                 max_chunk_res: int = 1 << 28, method: str = "grouped", place: Optional[dict] = None):
     """Annotation x k-mer count matrix as a COO list sorted by key = ann * S + code
     (keys int64 holding the uint64 pattern, vals int64).  Sequences with ann_id < 0 do not
     contribute (Totals come from the basis tables).
@@ -879,7 +881,11 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
     method "grouped" (default): the annotated sequences are gathered in annotation order and sorted one annotation
     slice at a time with 32-bit keys (skm_learn_sparse_group); "global": one 64-bit radix sort over all window keys of
     the shard (skm_learn_sparse, the first implementation, kept as a cross-check and for slices whose keys need more
-    than 32 bits)."""
+    than 32 bits).
+    place (grouped path only; learn_sparse_hybrid): dict(ins_ann, ins_cum, ins_pos int64 [H], totals int64 [S] or None,
+    extra int) — the list is written straight into a larger list with room for H foreign blocks
+    (skm_learn_sparse_group_place); returns (keys buffer, vals buffer, entries of THIS list) without slicing, or None when
+    the grouped path does not apply (the caller then places the list itself)."""
     tab = alphabet_tables(alphabet, batch.device)
     dev = batch.device
     ann_id = ann_id.to(device=dev, dtype=torch.int32).contiguous()
@@ -893,13 +899,16 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
         bounds = torch.searchsorted(sk, torch.tensor(starts, dtype=torch.int32, device=dev)).tolist()     # one sync
         n_sel = bounds[-1]
         if n_sel == 0:
+            if place:
+                cap = max(int(place["extra"]), 1)
+                return torch.empty(cap, dtype=torch.int64, device=dev), torch.empty(cap, dtype=torch.int64, device=dev), 0
             z = torch.zeros(0, dtype=torch.int64, device=dev)
             return z, z.clone()
         g_res, g_off = gather_sequences(batch, order[:n_sel])
         g_ann = sk[:n_sel].contiguous()
         edge = g_off[torch.tensor(bounds, dtype=torch.int64, device=dev)].tolist()
         if max(edge[i + 1] - (edge[i] & ~15) for i in range(len(starts) - 1)) < (1 << 31) - 64:
-            total = edge[-1]
+            total = edge[-1] + (int(place["extra"]) if place else 0)
             keys = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
             vals = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
             dn = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -915,12 +924,23 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
                     ws = None
                     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 offs = (g_off[s0:s1 + 1] - base).contiguous()
-                check(lib().skm_learn_sparse_group(_ptr(g_res[base:]), nres, _ptr(offs), s1 - s0, _ptr(tab.lut), tab.nsym, int(k),
-                                                   _ptr(g_ann[s0:s1]), starts[gi], starts[gi + 1] - starts[gi], _ptr(keys), _ptr(vals),
-                                                   total, _ptr(dn), _ptr(ws), ws.numel(), _stream()))
+                if place:
+                    check(lib().skm_learn_sparse_group_place(_ptr(g_res[base:]), nres, _ptr(offs), s1 - s0, _ptr(tab.lut), tab.nsym, int(k),
+                                                             _ptr(g_ann[s0:s1]), starts[gi], starts[gi + 1] - starts[gi], _ptr(keys), _ptr(vals),
+                                                             total, _ptr(dn), _ptr(place["ins_ann"]), _ptr(place["ins_cum"]),
+                                                             int(place["ins_ann"].numel()), _ptr(place["ins_pos"]), _ptr(place.get("totals")),
+                                                             _ptr(ws), ws.numel(), _stream()))
+                else:
+                    check(lib().skm_learn_sparse_group(_ptr(g_res[base:]), nres, _ptr(offs), s1 - s0, _ptr(tab.lut), tab.nsym, int(k),
+                                                       _ptr(g_ann[s0:s1]), starts[gi], starts[gi + 1] - starts[gi], _ptr(keys), _ptr(vals),
+                                                       total, _ptr(dn), _ptr(ws), ws.numel(), _stream()))
             m = int(dn.item())
             assert m <= total
+            if place:
+                return keys, vals, m
             return keys[:m].clone(), vals[:m].clone()
+    if place:
+        return None
     parts_k, parts_v = [], []
     for lo, hi in _chunks_by_residues(batch.offsets_host, max_chunk_res):
         sub = _sub_batch(batch, lo, hi)
@@ -1040,6 +1060,35 @@ def learn_sparse_hybrid(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Te
         ann_light = torch.where(is_heavy[safe], torch.full_like(ann_id, -1), ann_id)
     else:
         ann_light = ann_id
+    if H and os.environ.get("SKM_LEARN_PLACE", "1") != "0":
+        # The heavy blocks' sizes first (the rows are counted already), then the light list is sorted slice by slice and
+        # written STRAIGHT to its final places between the heavy blocks, adding its counts to the Totals on the way
+        # (skm_learn_sparse_group_place): no separate column-sum pass over the light list and no shift copy of it.
+        blk = lib().skm_rows_block()
+        nblk = (S + blk - 1) // blk
+        counts = torch.empty((H, nblk), dtype=torch.int32, device=dev)
+        check(lib().skm_rows_block_counts(_ptr(rows), H, S, _ptr(counts), _stream()))
+        c64 = counts.to(torch.int64)
+        incl = torch.cumsum(c64, dim=1)
+        blk_off = (incl - c64).contiguous()
+        row_nnz = incl[:, -1].contiguous()
+        cum = torch.cumsum(row_nnz, 0).contiguous()          # inclusive
+        heavy_total = int(cum[-1].item())                    # one sync
+        ins_pos = torch.full((H,), INT64_MAX, dtype=torch.int64, device=dev)
+        placed = learn_sparse(batch, alphabet, k, ann_light, n_ann,
+                              place=dict(ins_ann=heavy.contiguous(), ins_cum=cum, ins_pos=ins_pos, totals=totals, extra=heavy_total))
+        if placed is not None:
+            keys, vals, m_light = placed
+            if want_totals:
+                check(lib().skm_rows_colsum(_ptr(rows), rows.shape[0], S, _ptr(totals), _stream()))
+            # light entries in front of block h = the smallest recorded index over the blocks from h on (none: all of them)
+            tail = torch.cat([ins_pos, torch.tensor([m_light], dtype=torch.int64, device=dev)])
+            before = torch.flip(torch.cummin(torch.flip(tail, [0]), 0).values, [0])[:H]
+            row_dst = (before + cum - row_nnz).contiguous()
+            total = m_light + heavy_total
+            check(lib().skm_rows_emit(_ptr(rows), H, S, _ptr(blk_off), _ptr(row_dst), _ptr(heavy.contiguous()), _ptr(keys), _ptr(vals), total, _stream()))
+            keys, vals = keys[:total], vals[:total]
+            return (keys, vals, totals) if want_totals else (keys, vals)
     kl, vl = learn_sparse(batch, alphabet, k, ann_light, n_ann)
     if want_totals:
         check(lib().skm_coo_colsum(_ptr(kl), _ptr(vl), kl.numel(), S, _ptr(totals), _stream()))
