@@ -966,7 +966,7 @@ def learn_sparse(batch: SequenceBatch, alphabet, k: int, ann_id: torch.Tensor, n
 
 HEAVY_ROW_DIV = int(os.environ.get("SKM_HEAVY_ROW_DIV", "4"))   # an annotation is "heavy" when it has more residues than S / HEAVY_ROW_DIV ...
 HEAVY_ROWS_MAX_BYTES = 8 << 30   # ... as long as the dense rows of all heavy annotations stay below this
-ROWS_L2_BYTES = int(os.environ.get("SKM_ROWS_L2_MB", "40")) << 20   # rows counted by one skm_rows_accumulate launch (L2-resident counters)
+ROWS_L2_BYTES = int(os.environ.get("SKM_ROWS_L2_MB", "100")) << 20   # rows counted by one skm_rows_accumulate launch (L2-resident counters): ~0.8 of the 126 MB L2, from a sweep (profiles/R2al_*)
 
 
 def _learn_rows(batch: SequenceBatch, tab: AlphabetTables, k: int, ann_id: torch.Tensor, n_ann: int, S: int,
