@@ -123,6 +123,11 @@ def _worker(rank, world, port, tmp):
             start = int(np.sum(send_[:rank]))
             buf[offs_[rank]:offs_[rank] + send_[rank]] = keys_[start:start + send_[rank]]
         assert np.array_equal(buf, rk.numpy())
+        # ---- peer buffers that cannot be set up: every rank learns it in the same collective and the path switches off ---
+        os.environ["SKM_PEER_FAIL"] = "1"
+        pb = D.PeerBuffers()
+        assert pb.ensure(1000) is False and pb.disabled and pb.own is None and pb.ensure(10) is False
+        del os.environ["SKM_PEER_FAIL"]
         # ---- the same exchange with ranges balanced by entry count (Zipf-sized annotations) ------------------------
         zrng = np.random.default_rng(7 + rank)
         wz = 1.0 / np.arange(1, 41) ** 1.3
