@@ -224,7 +224,9 @@ class Ctx:
         # rank 0 samples the GPUs of ALL ranks (median clock over all samples, union of the throttle reasons)
         if os.environ.get("SKM_NO_CLOCKS"):            # experiment: is the sampler what perturbs 1-ms steps at 8 ranks?
             clocks = False
-        sampler = ClockSampler(",".join(str(i) for i in range(self.world))) if clocks and self.rank == 0 else None
+        vis = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+        ids = [vis[i] if i < len(vis) else str(i) for i in range(self.world)]        # nvidia-smi wants PHYSICAL indices / UUIDs
+        sampler = ClockSampler(",".join(ids)) if clocks and self.rank == 0 else None
         if sampler:
             sampler.start()                  # nvidia-smi needs ~100 ms per sample: it runs from the warm-up on
         for _ in range(max(warmup, 3)):
